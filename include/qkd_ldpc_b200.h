@@ -1,0 +1,171 @@
+/*
+ * qkd_ldpc_b200.h -- C-ABI of libqkdldpc_b200.so
+ *
+ * B200-native (sm_100a) replacement for the hot path of ColdCloudd/QKD_LDPC: syndrome-based LDPC
+ * information reconciliation by flooding sum-product belief propagation. Plain pointers and sizes
+ * only; no C++ or torch types cross this boundary. There is NO CPU fallback behind these entry
+ * points: every compute call fails with QLB_ERR_CUDA when no sm_100-class device is usable.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root). The host-side C++ mirror of the reference API (qkd_ldpc_b200/host/) and the
+ * Python binding (qkd_ldpc_b200/capi.py) are thin callers of exactly these functions.
+ *
+ * Conventions (same as the reference unless noted):
+ *   - a key / syndrome bit is 0 or 1; "unpacked" arrays hold one 32-bit int per bit
+ *     (src/array_and_matrix_operations.hpp:39-40); "packed" arrays hold 32 bits per uint32_t word,
+ *     bit i of a frame in word i/32 at bit position i%32, frames padded to whole words
+ *     (row stride qlb_code_words_n() / qlb_code_words_m() words);
+ *   - LLR sign: positive means bit 0 (src/qkd_ldpc_algorithm.cpp:259-266,401-405);
+ *   - node indices are 0-based (src/array_and_matrix_operations.cpp:255,276);
+ *   - all host buffers are owned by the caller; the library owns device scratch inside a context.
+ *
+ * Thread safety: a qlb_code is immutable after creation and may be shared; a qlb_ctx must be used
+ * by one host thread at a time (one context per GPU per thread, as the reference uses one scratch
+ * set per pool worker, src/simulation.cpp:230,244-250).
+ */
+#ifndef QKD_LDPC_B200_H
+#define QKD_LDPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLB_VERSION 100 /* 0.1.0 */
+
+/* status codes (0 = ok); qlb_last_error() gives the message of the calling thread's last failure */
+enum {
+    QLB_OK = 0,
+    QLB_ERR_INVALID = 1,     /* bad argument / inconsistent matrix                                  */
+    QLB_ERR_CUDA = 2,        /* CUDA runtime failure or no usable device                            */
+    QLB_ERR_UNSUPPORTED = 3, /* valid input the kernels do not handle (see message)                 */
+    QLB_ERR_KEY_TOO_SMALL = 4, /* floor(N*QBER) == 0: the reference throws here (src/simulation.cpp:170-175) */
+    QLB_ERR_NCCL = 5
+};
+
+/* message arithmetic */
+enum {
+    QLB_PRECISION_F64 = 64, /* the reference's arithmetic and operation order (tanh, divide, 2*atanh) */
+    QLB_PRECISION_F32 = 32  /* single precision, leave-one-out products (no reference counterpart)    */
+};
+
+/* qlb_decode_params.flags */
+enum {
+    QLB_FLAG_F32_FAST_MATH = 1 /* fp32 only: exp-domain check rule on MUFU ex2/lg2/rcp instead of tanhf/atanhf */
+};
+
+typedef struct qlb_code qlb_code; /* a parity-check matrix prepared for the device (replaces H_matrix on the device side) */
+typedef struct qlb_ctx qlb_ctx;   /* one GPU: stream, scratch, device copies of the codes it has seen */
+
+/* Mirrors what the reference reads from the global CFG inside the hot path
+ * (src/qkd_ldpc_algorithm.cpp:246,313,424-425; src/config.hpp:40-58). */
+typedef struct qlb_decode_params {
+    int32_t precision;        /* QLB_PRECISION_F64 | QLB_PRECISION_F32                              */
+    int32_t max_iterations;   /* CFG.SUM_PRODUCT_MAX_ITERATIONS, >= 1                               */
+    int32_t enable_threshold; /* CFG.ENABLE_SUM_PRODUCT_MSG_LLR_THRESHOLD                           */
+    int32_t flags;            /* QLB_FLAG_*                                                        */
+    double threshold;         /* CFG.SUM_PRODUCT_MSG_LLR_THRESHOLD, > 0 when enabled                */
+} qlb_decode_params;
+
+/* Per-frame result of a decode; mirrors SP_result / LDPC_result (src/qkd_ldpc_algorithm.hpp:14-24). */
+enum { QLB_RES_SYNDROMES_MATCH = 1, QLB_RES_KEYS_MATCH = 2 };
+
+int qlb_version(void);
+const char *qlb_last_error(void);
+
+/* Number of visible CUDA devices (0 when none); never fails. */
+int qlb_device_count(void);
+
+/* ---- code handle ------------------------------------------------------------------------------
+ * Replaces the device-facing role of `struct H_matrix` (src/array_and_matrix_operations.hpp:16-27).
+ * Input is the matrix flattened from that struct, both adjacency halves in stored order:
+ *   check_nodes[j][k] = col_idx[row_ptr[j] + k],  check_nodes_weight[j] = row_ptr[j+1] - row_ptr[j]
+ *   bit_nodes[i][k]   = row_idx[col_ptr[i] + k],  bit_nodes_weight[i]   = col_ptr[i+1] - col_ptr[i]
+ * The reference routes messages positionally (arrival counters, src/qkd_ldpc_algorithm.cpp:228-243,
+ * 300-311); creation replays those counters to fix the per-node operation order, and rejects
+ * (QLB_ERR_INVALID) matrices whose two halves do not describe the same edges in the same order
+ * -- the inputs on which the reference itself would misroute or overrun its rows.
+ */
+int qlb_code_create(int32_t n_bits, int32_t n_checks, const int32_t *row_ptr, const int32_t *col_idx,
+                    const int32_t *col_ptr, const int32_t *row_idx, qlb_code **code_out);
+void qlb_code_destroy(qlb_code *code);
+int32_t qlb_code_n(const qlb_code *code);       /* bit nodes   */
+int32_t qlb_code_m(const qlb_code *code);       /* check nodes */
+int32_t qlb_code_edges(const qlb_code *code);   /* edges       */
+int32_t qlb_code_words_n(const qlb_code *code); /* uint32 words per packed key      = ceil(n/32) */
+int32_t qlb_code_words_m(const qlb_code *code); /* uint32 words per packed syndrome = ceil(m/32) */
+
+/* Test/inspection hook: copies the device layout tables into caller buffers (any may be NULL).
+ *   slot_of_edge[e]  physical message slot of check-side edge e (CSR position)
+ *   bit_slots[a*n+i] physical slot of the a-th message of bit i in the reference's summation order
+ *                    (0xFFFFFFFF when a >= weight of bit i); a < qlb_code_max_bit_weight()
+ *   check_order[p]   original check index handled at sorted position p
+ */
+int32_t qlb_code_max_bit_weight(const qlb_code *code);
+int32_t qlb_code_max_check_weight(const qlb_code *code);
+int32_t qlb_code_slots(const qlb_code *code);
+int qlb_code_layout(const qlb_code *code, uint32_t *slot_of_edge, uint32_t *bit_slots, uint32_t *check_order);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int qlb_ctx_create(int device, qlb_ctx **ctx_out);
+void qlb_ctx_destroy(qlb_ctx *ctx);
+int qlb_ctx_device(const qlb_ctx *ctx);
+int qlb_ctx_sm_count(const qlb_ctx *ctx);
+/* The context's CUDA stream (a cudaStream_t) for callers that time or order work with their own events. */
+void *qlb_ctx_stream(const qlb_ctx *ctx);
+int qlb_ctx_synchronize(qlb_ctx *ctx);
+/* Decode-kernel launches and executed frame-iterations since the context was created / last reset. */
+int qlb_ctx_counters(qlb_ctx *ctx, uint64_t *kernel_launches, uint64_t *frame_iterations, int reset);
+/* CUDA-event stopwatch on the context's stream: start, enqueue work, stop -> elapsed milliseconds. */
+int qlb_ctx_timer_start(qlb_ctx *ctx);
+int qlb_ctx_timer_stop(qlb_ctx *ctx, float *elapsed_ms_out);
+
+/* ---- syndrome ---------------------------------------------------------------------------------
+ * Replaces calculate_syndrome_regular / calculate_syndrome_irregular
+ * (src/array_and_matrix_operations.cpp:463-473 / 476-486) for a batch of frames:
+ *   syndrome[f][j] = XOR_k bits[f][check_nodes[j][k]].
+ * Host buffers; bits [n_frames][n], syndrome_out [n_frames][m] (unpacked) or word-padded (packed).
+ */
+int qlb_syndrome_batch(qlb_ctx *ctx, const qlb_code *code, int64_t n_frames, const int32_t *bits, int32_t *syndrome_out);
+int qlb_syndrome_batch_packed(qlb_ctx *ctx, const qlb_code *code, int64_t n_frames, const uint32_t *bits_packed,
+                              uint32_t *syndrome_packed_out);
+
+/* ---- sum-product decode ------------------------------------------------------------------------
+ * Replaces sum_product_decoding_regular / _irregular (src/qkd_ldpc_algorithm.cpp:3-173 / 175-345)
+ * for a batch: a-priori LLRs llr[f][n] (double, as in the reference signature), target syndromes
+ * syndrome[f][m] (unpacked). Outputs per frame: bits_out[f][n] (last hard decision, unpacked; may be
+ * NULL), iterations_out[f] (SP_result.iterations_num), result_out[f] (QLB_RES_SYNDROMES_MATCH bit).
+ */
+int qlb_sum_product_batch(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                          const double *llr, const int32_t *syndrome, int32_t *bits_out, uint32_t *iterations_out,
+                          uint8_t *result_out);
+
+/* ---- reconciliation ----------------------------------------------------------------------------
+ * Replaces QKD_LDPC_regular / QKD_LDPC_irregular (src/qkd_ldpc_algorithm.cpp:347-396 / 398-447) for a
+ * batch: per frame, prior +-ln((1-q)/q) from Bob's bits, Alice's syndrome, decode, key compare --
+ * fused in one kernel. qber[f] is the frame's exact error ratio (src/simulation.cpp:169,183), must be
+ * in (0,1). Outputs: iterations_out[f], result_out[f] (QLB_RES_* bits), optional decoded key
+ * (which the reference computes and discards, :444) and optional Alice syndrome.
+ */
+int qlb_reconcile_batch(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                        const int32_t *alice, const int32_t *bob, const double *qber, uint32_t *iterations_out,
+                        uint8_t *result_out, int32_t *decoded_out, int32_t *syndrome_out);
+int qlb_reconcile_batch_packed(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                               const uint32_t *alice_packed, const uint32_t *bob_packed, const double *qber,
+                               uint32_t *iterations_out, uint8_t *result_out, uint32_t *decoded_packed_out,
+                               uint32_t *syndrome_packed_out);
+
+/* Same operation on DEVICE-resident packed buffers (all pointers are device pointers on the context's
+ * GPU; log_prior[f] = ln((1-q)/q) as a double). Enqueued on the context's stream, returns without
+ * synchronizing. This is the entry the frame-batch scheduler and bench.py's device-resident leg use. */
+int qlb_reconcile_device(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                         const uint32_t *d_alice_packed, const uint32_t *d_bob_packed, const double *d_log_prior,
+                         uint32_t *d_iterations_out, uint8_t *d_result_out, uint32_t *d_decoded_packed_out,
+                         uint32_t *d_syndrome_packed_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QKD_LDPC_B200_H */

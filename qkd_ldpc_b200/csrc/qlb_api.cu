@@ -1,0 +1,679 @@
+// C-ABI of libqkdldpc_b200.so (declared in include/qkd_ldpc_b200.h): code handles, per-GPU contexts, and the batch
+// entry points that replace the reference's per-frame hot-path functions. No CPU compute path exists here: every
+// entry that does work launches the sm_100a kernels in qlb_kernels.cuh or fails.
+#include "../../include/qkd_ldpc_b200.h"
+#include "qlb_kernels.cuh"
+#include "qlb_layout.hpp"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace qlb;
+
+namespace
+{
+    thread_local std::string g_error;
+    int fail(int code, const std::string &msg)
+    {
+        g_error = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *what)
+    {
+        return fail(QLB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+#define QLB_CUDA(call)                                   \
+    do                                                   \
+    {                                                    \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess)                          \
+            return cuda_fail(e__, #call);                \
+    } while (0)
+
+    std::atomic<uint64_t> g_next_code_id{1};
+}
+
+struct qlb_code
+{
+    uint64_t id;
+    CodeLayout L;
+};
+
+namespace
+{
+    struct DeviceCode
+    {
+        CodeDev dev{};
+        std::vector<void *> allocs;
+    };
+
+    // grow-only device buffer
+    struct DevBuf
+    {
+        void *p = nullptr;
+        size_t cap = 0;
+        cudaError_t reserve(size_t bytes)
+        {
+            if (bytes <= cap)
+                return cudaSuccess;
+            if (p)
+                cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e == cudaSuccess)
+                cap = bytes;
+            return e;
+        }
+        void release()
+        {
+            if (p)
+                cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+    };
+}
+
+struct qlb_ctx
+{
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    unsigned long long *d_counters = nullptr; // [0] frame queue, [1] executed iterations
+    uint64_t launches = 0;
+    std::map<uint64_t, DeviceCode> codes;
+    DevBuf scratch, in_a, in_b, in_q, in_llr, in_syn, out_it, out_res, out_dec, out_syn;
+    std::vector<double> host_logp;
+    std::vector<uint32_t> host_pack_a, host_pack_b, host_pack_out;
+};
+
+namespace
+{
+    int upload(const void *src, size_t bytes, DeviceCode &dc, const void **dst_out)
+    {
+        void *d = nullptr;
+        QLB_CUDA(cudaMalloc(&d, bytes ? bytes : 4));
+        dc.allocs.push_back(d);
+        if (bytes)
+            QLB_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        *dst_out = d;
+        return QLB_OK;
+    }
+
+    int get_device_code(qlb_ctx *ctx, const qlb_code *code, const CodeDev **out)
+    {
+        auto it = ctx->codes.find(code->id);
+        if (it != ctx->codes.end())
+        {
+            *out = &it->second.dev;
+            return QLB_OK;
+        }
+        const CodeLayout &L = code->L;
+        DeviceCode dc;
+        CodeDev &d = dc.dev;
+        d.n = L.n;
+        d.m = L.m;
+        d.e = L.e;
+        d.words_n = L.words_n;
+        d.words_m = L.words_m;
+        d.max_check_w = L.max_check_w;
+        d.max_bit_w = L.max_bit_w;
+        for (int k = 0; k < kMaxCW; ++k)
+        {
+            d.cnt[k] = k < L.max_check_w ? L.cnt[k] : 0;
+            d.base[k] = k < L.max_check_w ? L.base[k] : 0;
+        }
+        int rc;
+        const void *p = nullptr;
+        if (L.e < 65535)
+        {
+            std::vector<uint16_t> s16(L.bit_slots.size());
+            for (size_t i = 0; i < s16.size(); ++i)
+                s16[i] = L.bit_slots[i] == kNoSlot ? 0xFFFFu : static_cast<uint16_t>(L.bit_slots[i]);
+            if ((rc = upload(s16.data(), s16.size() * 2, dc, &p)))
+                return rc;
+            d.bit_slots16 = static_cast<const uint16_t *>(p);
+        }
+        if ((rc = upload(L.bit_slots.data(), L.bit_slots.size() * 4, dc, &p)))
+            return rc;
+        d.bit_slots32 = static_cast<const uint32_t *>(p);
+        if ((rc = upload(L.check_order.data(), L.check_order.size() * 4, dc, &p)))
+            return rc;
+        d.check_order = static_cast<const uint32_t *>(p);
+        if ((rc = upload(L.row_ptr.data(), L.row_ptr.size() * 4, dc, &p)))
+            return rc;
+        d.row_ptr = static_cast<const int32_t *>(p);
+        if ((rc = upload(L.col_idx.data(), L.col_idx.size() * 4, dc, &p)))
+            return rc;
+        d.col_idx = static_cast<const int32_t *>(p);
+        auto ins = ctx->codes.emplace(code->id, std::move(dc));
+        *out = &ins.first->second.dev;
+        return QLB_OK;
+    }
+
+    int check_params(const qlb_decode_params *p)
+    {
+        if (!p)
+            return fail(QLB_ERR_INVALID, "decode params are null");
+        if (p->precision != QLB_PRECISION_F64 && p->precision != QLB_PRECISION_F32)
+            return fail(QLB_ERR_INVALID, "precision must be 64 or 32");
+        if (p->max_iterations < 1)
+            return fail(QLB_ERR_INVALID, "Minimum number of sum-product iterations must be >= 1!");
+        if (p->enable_threshold && !(p->threshold > 0.))
+            return fail(QLB_ERR_INVALID, "Sum-product message LLR threshold must be > 0!");
+        if ((p->flags & QLB_FLAG_F32_FAST_MATH) && p->precision != QLB_PRECISION_F32)
+            return fail(QLB_ERR_INVALID, "QLB_FLAG_F32_FAST_MATH requires fp32 precision");
+        return QLB_OK;
+    }
+
+    // ---- kernel selection ---------------------------------------------------------------------------------------
+    template <typename Math, int kTier, bool kReconcile, int kShapeW, int kThreads>
+    int launch_one(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        typedef typename Math::real Real;
+        auto kern = decode_kernel<Math, kTier, kReconcile, kShapeW, kThreads>;
+        const Carve cv = make_carve<Real, kTier>(args.code.n, args.code.m, args.code.e, args.code.max_bit_w);
+        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total_smem));
+        int per_sm = 0;
+        QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, cv.total_smem));
+        if (per_sm < 1)
+            return fail(QLB_ERR_UNSUPPORTED, "decode kernel does not fit on an SM for this code");
+        long long grid = (long long)ctx->sm_count * per_sm;
+        if (grid > args.n_frames)
+            grid = args.n_frames;
+        if (cv.total_scratch)
+        {
+            QLB_CUDA(ctx->scratch.reserve((size_t)grid * cv.total_scratch));
+            args.scratch = static_cast<unsigned char *>(ctx->scratch.p);
+            args.scratch_stride = cv.total_scratch;
+        }
+        QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+        args.queue = ctx->d_counters;
+        args.iter_total = ctx->d_counters + 1;
+        kern<<<(unsigned)grid, kThreads, cv.total_smem, ctx->stream>>>(args);
+        QLB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+        return QLB_OK;
+    }
+
+    template <typename Math, int kTier, bool kReconcile, int kThreads>
+    int launch_shape(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        const int cw = args.code.max_check_w, bw = args.code.max_bit_w;
+        if (kTier != kTierGlobal && bw <= 4 && cw <= 8)
+            return launch_one<Math, kTier, kReconcile, 8, kThreads>(ctx, args);
+        if (kTier != kTierGlobal && bw <= 4 && cw <= 16)
+            return launch_one<Math, kTier, kReconcile, 16, kThreads>(ctx, args);
+        return launch_one<Math, kTier, kReconcile, 0, kThreads>(ctx, args);
+    }
+
+    template <typename Math, bool kReconcile>
+    int launch_tier(qlb_ctx *ctx, DecodeArgs &args, int forced_tier)
+    {
+        typedef typename Math::real Real;
+        const CodeDev &c = args.code;
+        const bool idx16 = c.e < 65535 && c.bit_slots16 != nullptr;
+        const size_t all = make_carve<Real, kTierSmemAll>(c.n, c.m, c.e, c.max_bit_w).total_smem;
+        const size_t idx = make_carve<Real, kTierSmemIdx>(c.n, c.m, c.e, c.max_bit_w).total_smem;
+        int tier = kTierGlobal;
+        if (idx16 && idx <= (size_t)ctx->smem_optin)
+            tier = kTierSmemIdx;
+        if (idx16 && sizeof(Real) == 4 && all <= (size_t)ctx->smem_optin)
+            tier = kTierSmemAll;
+        if (forced_tier >= 0 && forced_tier >= tier)
+            tier = forced_tier; // tests may force a slower tier, never one that does not fit
+        if (sizeof(Real) == 4)
+        {
+            if (tier == kTierSmemAll)
+                return launch_shape<Math, kTierSmemAll, kReconcile, 1024>(ctx, args);
+        }
+        if (tier == kTierSmemIdx)
+            return launch_shape<Math, kTierSmemIdx, kReconcile, 512>(ctx, args);
+        return launch_shape<Math, kTierGlobal, kReconcile, 512>(ctx, args);
+    }
+
+    template <bool kReconcile>
+    int launch_decode(qlb_ctx *ctx, const qlb_decode_params *p, DecodeArgs &args)
+    {
+        args.max_it = p->max_iterations;
+        args.enable_thr = p->enable_threshold;
+        args.thr = p->threshold;
+        const int forced = (p->flags >> 8) & 0xF ? ((p->flags >> 8) & 0xF) - 1 : -1; // bits 8..11: test hook, tier+1
+        if (p->precision == QLB_PRECISION_F64)
+            return launch_tier<MathF64, kReconcile>(ctx, args, forced);
+        if (p->flags & QLB_FLAG_F32_FAST_MATH)
+            return launch_tier<MathF32Fast, kReconcile>(ctx, args, forced);
+        return launch_tier<MathF32, kReconcile>(ctx, args, forced);
+    }
+
+    int launch_syndrome(qlb_ctx *ctx, const CodeDev &dev, long long n_frames, const uint32_t *d_bits, uint32_t *d_out)
+    {
+        const size_t per_frame = (size_t)dev.words_n * 4;
+        int group = kSynFrames, stage = 1;
+        const size_t budget = 96 * 1024;
+        if (per_frame > budget)
+        {
+            group = 1;
+            stage = 0;
+        }
+        else
+            while ((size_t)group * per_frame > budget)
+                group >>= 1;
+        const size_t smem = stage ? (size_t)group * per_frame : 0;
+        QLB_CUDA(cudaFuncSetAttribute(syndrome_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        const long long grid = (n_frames + group - 1) / group;
+        syndrome_kernel<<<(unsigned)grid, kSynThreads, smem, ctx->stream>>>(dev, n_frames, group, stage, d_bits, d_out);
+        QLB_CUDA(cudaGetLastError());
+        return QLB_OK;
+    }
+
+    void pack_frames(const int32_t *bits, int64_t frames, int n, int words, uint32_t *out)
+    {
+        for (int64_t f = 0; f < frames; ++f)
+        {
+            const int32_t *src = bits + f * n;
+            uint32_t *dst = out + f * words;
+            for (int w = 0; w < words; ++w)
+            {
+                uint32_t v = 0;
+                const int lim = n - w * 32 < 32 ? n - w * 32 : 32;
+                for (int b = 0; b < lim; ++b)
+                    v |= static_cast<uint32_t>(src[w * 32 + b] & 1) << b;
+                dst[w] = v;
+            }
+        }
+    }
+    void unpack_frames(const uint32_t *packed, int64_t frames, int n, int words, int32_t *out)
+    {
+        for (int64_t f = 0; f < frames; ++f)
+            for (int i = 0; i < n; ++i)
+                out[f * n + i] = static_cast<int32_t>((packed[f * words + (i >> 5)] >> (i & 31)) & 1u);
+    }
+}
+
+extern "C"
+{
+    int qlb_version(void) { return QLB_VERSION; }
+    const char *qlb_last_error(void) { return g_error.c_str(); }
+
+    int qlb_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    int qlb_code_create(int32_t n_bits, int32_t n_checks, const int32_t *row_ptr, const int32_t *col_idx,
+                        const int32_t *col_ptr, const int32_t *row_idx, qlb_code **code_out)
+    {
+        if (!code_out)
+            return fail(QLB_ERR_INVALID, "code_out is null");
+        *code_out = nullptr;
+        qlb_code *c = new qlb_code();
+        const std::string err = c->L.build(n_bits, n_checks, row_ptr, col_idx, col_ptr, row_idx);
+        if (!err.empty())
+        {
+            delete c;
+            return fail(QLB_ERR_INVALID, err);
+        }
+        c->id = g_next_code_id.fetch_add(1);
+        *code_out = c;
+        return QLB_OK;
+    }
+    void qlb_code_destroy(qlb_code *code) { delete code; }
+    int32_t qlb_code_n(const qlb_code *c) { return c ? c->L.n : 0; }
+    int32_t qlb_code_m(const qlb_code *c) { return c ? c->L.m : 0; }
+    int32_t qlb_code_edges(const qlb_code *c) { return c ? c->L.e : 0; }
+    int32_t qlb_code_words_n(const qlb_code *c) { return c ? c->L.words_n : 0; }
+    int32_t qlb_code_words_m(const qlb_code *c) { return c ? c->L.words_m : 0; }
+    int32_t qlb_code_max_bit_weight(const qlb_code *c) { return c ? c->L.max_bit_w : 0; }
+    int32_t qlb_code_max_check_weight(const qlb_code *c) { return c ? c->L.max_check_w : 0; }
+    int32_t qlb_code_slots(const qlb_code *c) { return c ? c->L.e : 0; }
+    int qlb_code_layout(const qlb_code *c, uint32_t *slot_of_edge, uint32_t *bit_slots, uint32_t *check_order)
+    {
+        if (!c)
+            return fail(QLB_ERR_INVALID, "code is null");
+        if (slot_of_edge)
+            std::memcpy(slot_of_edge, c->L.slot_of_edge.data(), c->L.slot_of_edge.size() * 4);
+        if (bit_slots)
+            std::memcpy(bit_slots, c->L.bit_slots.data(), c->L.bit_slots.size() * 4);
+        if (check_order)
+            std::memcpy(check_order, c->L.check_order.data(), c->L.check_order.size() * 4);
+        return QLB_OK;
+    }
+
+    int qlb_ctx_create(int device, qlb_ctx **ctx_out)
+    {
+        if (!ctx_out)
+            return fail(QLB_ERR_INVALID, "ctx_out is null");
+        *ctx_out = nullptr;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+        {
+            cudaGetLastError();
+            return fail(QLB_ERR_CUDA, "no CUDA device is available: libqkdldpc_b200 has no CPU path");
+        }
+        if (device < 0 || device >= count)
+            return fail(QLB_ERR_INVALID, "device index out of range");
+        cudaDeviceProp prop;
+        QLB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(QLB_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
+        QLB_CUDA(cudaSetDevice(device));
+        qlb_ctx *ctx = new qlb_ctx();
+        ctx->device = device;
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess ||
+            (e = cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+            (e = cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long))) != cudaSuccess)
+        {
+            qlb_ctx_destroy(ctx);
+            return cuda_fail(e, "context setup");
+        }
+        *ctx_out = ctx;
+        return QLB_OK;
+    }
+
+    void qlb_ctx_destroy(qlb_ctx *ctx)
+    {
+        if (!ctx)
+            return;
+        cudaSetDevice(ctx->device);
+        if (ctx->stream)
+            cudaStreamSynchronize(ctx->stream);
+        for (auto &kv : ctx->codes)
+            for (void *p : kv.second.allocs)
+                cudaFree(p);
+        for (DevBuf *b : {&ctx->scratch, &ctx->in_a, &ctx->in_b, &ctx->in_q, &ctx->in_llr, &ctx->in_syn, &ctx->out_it,
+                          &ctx->out_res, &ctx->out_dec, &ctx->out_syn})
+            b->release();
+        if (ctx->d_counters)
+            cudaFree(ctx->d_counters);
+        if (ctx->ev_start)
+            cudaEventDestroy(ctx->ev_start);
+        if (ctx->ev_stop)
+            cudaEventDestroy(ctx->ev_stop);
+        if (ctx->stream)
+            cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    }
+
+    int qlb_ctx_device(const qlb_ctx *ctx) { return ctx ? ctx->device : -1; }
+    int qlb_ctx_sm_count(const qlb_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+    void *qlb_ctx_stream(const qlb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+    int qlb_ctx_synchronize(qlb_ctx *ctx)
+    {
+        if (!ctx)
+            return fail(QLB_ERR_INVALID, "ctx is null");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return QLB_OK;
+    }
+    int qlb_ctx_counters(qlb_ctx *ctx, uint64_t *kernel_launches, uint64_t *frame_iterations, int reset)
+    {
+        if (!ctx)
+            return fail(QLB_ERR_INVALID, "ctx is null");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        unsigned long long it = 0;
+        QLB_CUDA(cudaMemcpy(&it, ctx->d_counters + 1, sizeof(it), cudaMemcpyDeviceToHost));
+        if (kernel_launches)
+            *kernel_launches = ctx->launches;
+        if (frame_iterations)
+            *frame_iterations = it;
+        if (reset)
+        {
+            ctx->launches = 0;
+            QLB_CUDA(cudaMemset(ctx->d_counters + 1, 0, sizeof(unsigned long long)));
+        }
+        return QLB_OK;
+    }
+    int qlb_ctx_timer_start(qlb_ctx *ctx)
+    {
+        if (!ctx)
+            return fail(QLB_ERR_INVALID, "ctx is null");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        QLB_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+        return QLB_OK;
+    }
+    int qlb_ctx_timer_stop(qlb_ctx *ctx, float *elapsed_ms_out)
+    {
+        if (!ctx || !elapsed_ms_out)
+            return fail(QLB_ERR_INVALID, "ctx or output is null");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        QLB_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+        QLB_CUDA(cudaEventSynchronize(ctx->ev_stop));
+        QLB_CUDA(cudaEventElapsedTime(elapsed_ms_out, ctx->ev_start, ctx->ev_stop));
+        return QLB_OK;
+    }
+
+    // ---- syndrome ---------------------------------------------------------------------------------------------------
+    int qlb_syndrome_batch_packed(qlb_ctx *ctx, const qlb_code *code, int64_t n_frames, const uint32_t *bits_packed,
+                                  uint32_t *syndrome_packed_out)
+    {
+        if (!ctx || !code || n_frames < 0 || (n_frames > 0 && (!bits_packed || !syndrome_packed_out)))
+            return fail(QLB_ERR_INVALID, "qlb_syndrome_batch_packed: null argument or negative frame count");
+        if (n_frames == 0)
+            return QLB_OK;
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const CodeDev *dev;
+        int rc = get_device_code(ctx, code, &dev);
+        if (rc)
+            return rc;
+        const size_t in_bytes = (size_t)n_frames * dev->words_n * 4, out_bytes = (size_t)n_frames * dev->words_m * 4;
+        QLB_CUDA(ctx->in_a.reserve(in_bytes));
+        QLB_CUDA(ctx->out_syn.reserve(out_bytes));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_a.p, bits_packed, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = launch_syndrome(ctx, *dev, n_frames, (const uint32_t *)ctx->in_a.p, (uint32_t *)ctx->out_syn.p)))
+            return rc;
+        QLB_CUDA(cudaMemcpyAsync(syndrome_packed_out, ctx->out_syn.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return QLB_OK;
+    }
+
+    int qlb_syndrome_batch(qlb_ctx *ctx, const qlb_code *code, int64_t n_frames, const int32_t *bits, int32_t *syndrome_out)
+    {
+        if (!ctx || !code || n_frames < 0 || (n_frames > 0 && (!bits || !syndrome_out)))
+            return fail(QLB_ERR_INVALID, "qlb_syndrome_batch: null argument or negative frame count");
+        if (n_frames == 0)
+            return QLB_OK;
+        const CodeLayout &L = code->L;
+        ctx->host_pack_a.resize((size_t)n_frames * L.words_n);
+        ctx->host_pack_out.resize((size_t)n_frames * L.words_m);
+        pack_frames(bits, n_frames, L.n, L.words_n, ctx->host_pack_a.data());
+        int rc = qlb_syndrome_batch_packed(ctx, code, n_frames, ctx->host_pack_a.data(), ctx->host_pack_out.data());
+        if (rc)
+            return rc;
+        unpack_frames(ctx->host_pack_out.data(), n_frames, L.m, L.words_m, syndrome_out);
+        return QLB_OK;
+    }
+
+    // ---- reconcile --------------------------------------------------------------------------------------------------
+    int qlb_reconcile_device(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                             const uint32_t *d_alice_packed, const uint32_t *d_bob_packed, const double *d_log_prior,
+                             uint32_t *d_iterations_out, uint8_t *d_result_out, uint32_t *d_decoded_packed_out,
+                             uint32_t *d_syndrome_packed_out)
+    {
+        if (!ctx || !code || n_frames < 0)
+            return fail(QLB_ERR_INVALID, "qlb_reconcile_device: null context/code or negative frame count");
+        int rc = check_params(params);
+        if (rc)
+            return rc;
+        if (n_frames == 0)
+            return QLB_OK;
+        if (!d_alice_packed || !d_bob_packed || !d_log_prior || !d_iterations_out || !d_result_out)
+            return fail(QLB_ERR_INVALID, "qlb_reconcile_device: null device buffer");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const CodeDev *dev;
+        if ((rc = get_device_code(ctx, code, &dev)))
+            return rc;
+        DecodeArgs args{};
+        args.code = *dev;
+        args.n_frames = n_frames;
+        args.alice = d_alice_packed;
+        args.bob = d_bob_packed;
+        args.log_prior = d_log_prior;
+        args.iterations = d_iterations_out;
+        args.result = d_result_out;
+        args.decoded = d_decoded_packed_out;
+        args.syndrome_out = d_syndrome_packed_out;
+        return launch_decode<true>(ctx, params, args);
+    }
+
+    int qlb_reconcile_batch_packed(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                                   const uint32_t *alice_packed, const uint32_t *bob_packed, const double *qber,
+                                   uint32_t *iterations_out, uint8_t *result_out, uint32_t *decoded_packed_out,
+                                   uint32_t *syndrome_packed_out)
+    {
+        if (!ctx || !code || n_frames < 0)
+            return fail(QLB_ERR_INVALID, "qlb_reconcile_batch_packed: null context/code or negative frame count");
+        int rc = check_params(params);
+        if (rc)
+            return rc;
+        if (n_frames == 0)
+            return QLB_OK;
+        if (!alice_packed || !bob_packed || !qber || !iterations_out || !result_out)
+            return fail(QLB_ERR_INVALID, "qlb_reconcile_batch_packed: null host buffer");
+        const CodeLayout &L = code->L;
+        // ln((1-q)/q) on the host in double, exactly as the reference forms it (src/qkd_ldpc_algorithm.cpp:400)
+        ctx->host_logp.resize((size_t)n_frames);
+        for (int64_t f = 0; f < n_frames; ++f)
+        {
+            const double q = qber[f];
+            if (q == 0.)
+                return fail(QLB_ERR_KEY_TOO_SMALL, "Key size '" + std::to_string(L.n) + "' is too small for QBER.");
+            if (!(q > 0. && q < 1.))
+                return fail(QLB_ERR_INVALID, "QBER must be: 0 < QBER < 1");
+            ctx->host_logp[(size_t)f] = std::log((1. - q) / q);
+        }
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const size_t key_bytes = (size_t)n_frames * L.words_n * 4, syn_bytes = (size_t)n_frames * L.words_m * 4;
+        QLB_CUDA(ctx->in_a.reserve(key_bytes));
+        QLB_CUDA(ctx->in_b.reserve(key_bytes));
+        QLB_CUDA(ctx->in_q.reserve((size_t)n_frames * 8));
+        QLB_CUDA(ctx->out_it.reserve((size_t)n_frames * 4));
+        QLB_CUDA(ctx->out_res.reserve((size_t)n_frames));
+        if (decoded_packed_out)
+            QLB_CUDA(ctx->out_dec.reserve(key_bytes));
+        if (syndrome_packed_out)
+            QLB_CUDA(ctx->out_syn.reserve(syn_bytes));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_a.p, alice_packed, key_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_b.p, bob_packed, key_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_q.p, ctx->host_logp.data(), (size_t)n_frames * 8, cudaMemcpyHostToDevice, ctx->stream));
+        rc = qlb_reconcile_device(ctx, code, params, n_frames, (const uint32_t *)ctx->in_a.p, (const uint32_t *)ctx->in_b.p,
+                                  (const double *)ctx->in_q.p, (uint32_t *)ctx->out_it.p, (uint8_t *)ctx->out_res.p,
+                                  decoded_packed_out ? (uint32_t *)ctx->out_dec.p : nullptr,
+                                  syndrome_packed_out ? (uint32_t *)ctx->out_syn.p : nullptr);
+        if (rc)
+            return rc;
+        QLB_CUDA(cudaMemcpyAsync(iterations_out, ctx->out_it.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(result_out, ctx->out_res.p, (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+        if (decoded_packed_out)
+            QLB_CUDA(cudaMemcpyAsync(decoded_packed_out, ctx->out_dec.p, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (syndrome_packed_out)
+            QLB_CUDA(cudaMemcpyAsync(syndrome_packed_out, ctx->out_syn.p, syn_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return QLB_OK;
+    }
+
+    int qlb_reconcile_batch(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                            const int32_t *alice, const int32_t *bob, const double *qber, uint32_t *iterations_out,
+                            uint8_t *result_out, int32_t *decoded_out, int32_t *syndrome_out)
+    {
+        if (!ctx || !code || n_frames < 0)
+            return fail(QLB_ERR_INVALID, "qlb_reconcile_batch: null context/code or negative frame count");
+        if (n_frames == 0)
+            return check_params(params);
+        if (!alice || !bob)
+            return fail(QLB_ERR_INVALID, "qlb_reconcile_batch: null key buffer");
+        const CodeLayout &L = code->L;
+        ctx->host_pack_a.resize((size_t)n_frames * L.words_n);
+        ctx->host_pack_b.resize((size_t)n_frames * L.words_n);
+        pack_frames(alice, n_frames, L.n, L.words_n, ctx->host_pack_a.data());
+        pack_frames(bob, n_frames, L.n, L.words_n, ctx->host_pack_b.data());
+        std::vector<uint32_t> dec, syn;
+        if (decoded_out)
+            dec.resize((size_t)n_frames * L.words_n);
+        if (syndrome_out)
+            syn.resize((size_t)n_frames * L.words_m);
+        int rc = qlb_reconcile_batch_packed(ctx, code, params, n_frames, ctx->host_pack_a.data(), ctx->host_pack_b.data(), qber,
+                                            iterations_out, result_out, decoded_out ? dec.data() : nullptr,
+                                            syndrome_out ? syn.data() : nullptr);
+        if (rc)
+            return rc;
+        if (decoded_out)
+            unpack_frames(dec.data(), n_frames, L.n, L.words_n, decoded_out);
+        if (syndrome_out)
+            unpack_frames(syn.data(), n_frames, L.m, L.words_m, syndrome_out);
+        return QLB_OK;
+    }
+
+    // ---- sum-product ------------------------------------------------------------------------------------------------
+    int qlb_sum_product_batch(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames,
+                              const double *llr, const int32_t *syndrome, int32_t *bits_out, uint32_t *iterations_out,
+                              uint8_t *result_out)
+    {
+        if (!ctx || !code || n_frames < 0)
+            return fail(QLB_ERR_INVALID, "qlb_sum_product_batch: null context/code or negative frame count");
+        int rc = check_params(params);
+        if (rc)
+            return rc;
+        if (n_frames == 0)
+            return QLB_OK;
+        if (!llr || !syndrome || !iterations_out || !result_out)
+            return fail(QLB_ERR_INVALID, "qlb_sum_product_batch: null host buffer");
+        const CodeLayout &L = code->L;
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const CodeDev *dev;
+        if ((rc = get_device_code(ctx, code, &dev)))
+            return rc;
+        ctx->host_pack_a.resize((size_t)n_frames * L.words_m);
+        pack_frames(syndrome, n_frames, L.m, L.words_m, ctx->host_pack_a.data());
+        const size_t llr_bytes = (size_t)n_frames * L.n * 8, syn_bytes = (size_t)n_frames * L.words_m * 4,
+                     key_bytes = (size_t)n_frames * L.words_n * 4;
+        QLB_CUDA(ctx->in_llr.reserve(llr_bytes));
+        QLB_CUDA(ctx->in_syn.reserve(syn_bytes));
+        QLB_CUDA(ctx->out_it.reserve((size_t)n_frames * 4));
+        QLB_CUDA(ctx->out_res.reserve((size_t)n_frames));
+        QLB_CUDA(ctx->out_dec.reserve(key_bytes));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_llr.p, llr, llr_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_syn.p, ctx->host_pack_a.data(), syn_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        DecodeArgs args{};
+        args.code = *dev;
+        args.n_frames = n_frames;
+        args.llr = (const double *)ctx->in_llr.p;
+        args.syndrome_in = (const uint32_t *)ctx->in_syn.p;
+        args.iterations = (uint32_t *)ctx->out_it.p;
+        args.result = (uint8_t *)ctx->out_res.p;
+        args.decoded = (uint32_t *)ctx->out_dec.p;
+        if ((rc = launch_decode<false>(ctx, params, args)))
+            return rc;
+        QLB_CUDA(cudaMemcpyAsync(iterations_out, ctx->out_it.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(result_out, ctx->out_res.p, (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+        if (bits_out)
+        {
+            ctx->host_pack_out.resize((size_t)n_frames * L.words_n);
+            QLB_CUDA(cudaMemcpyAsync(ctx->host_pack_out.data(), ctx->out_dec.p, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (bits_out)
+            unpack_frames(ctx->host_pack_out.data(), n_frames, L.n, L.words_n, bits_out);
+        return QLB_OK;
+    }
+}

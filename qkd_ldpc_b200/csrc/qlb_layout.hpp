@@ -1,0 +1,155 @@
+// Host-side preparation of a parity-check matrix for the decode kernels.
+//
+// The reference keeps H as two jagged adjacency halves (struct H_matrix,
+// /root/reference/src/array_and_matrix_operations.hpp:16-27) and routes messages POSITIONALLY:
+// a check appends its outgoing message to the next free slot of the receiving bit and vice versa
+// (/root/reference/src/qkd_ldpc_algorithm.cpp:228-243, 300-311). The per-node operation order that
+// results (product over a check's list left to right; sum over a bit's arrivals in check-scan order)
+// is what has to be reproduced for bit-exact fp64 messages. CodeLayout replays those arrival counters
+// once on the host and turns them into flat tables:
+//
+//   * physical message slots: checks are sorted by weight (descending, stable) and the k-th edge of the
+//     check at sorted position p lives at slot base[k] + p. Consecutive threads (consecutive p) touch
+//     consecutive addresses, so the check pass is bank-conflict free in shared memory and coalesced in
+//     global memory, and no per-check offset table is needed: weight(p) = #{k : cnt[k] > p}.
+//   * bit_slots[a][i]: slot holding the a-th message of bit i in the reference's summation order.
+//
+// One in-place message array is enough because a check reads and overwrites only its own slots and a
+// bit reads and overwrites only the slots of its own edges.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace qlb
+{
+    constexpr int kMaxCheckWeight = 64; // cnt[]/base[] travel in kernel parameters
+    constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+
+    struct CodeLayout
+    {
+        int32_t n = 0, m = 0, e = 0;
+        int32_t max_check_w = 0, max_bit_w = 0;
+        int32_t words_n = 0, words_m = 0;
+        std::vector<int32_t> row_ptr, col_idx;   // check half as given (syndrome kernel)
+        std::vector<uint32_t> cnt, base;         // [max_check_w]: checks with weight > k; slot offset of edge position k
+        std::vector<uint32_t> check_order;       // [m] original check index at sorted position p
+        std::vector<uint32_t> check_pos;         // [m] sorted position of original check j
+        std::vector<uint32_t> slot_of_edge;      // [e] physical slot of CSR position
+        std::vector<uint32_t> bit_slots;         // [max_bit_w * n], kNoSlot padded
+        std::vector<uint32_t> col_of_slot;       // [e] bit index of the edge stored at a slot
+
+        // Returns an empty string on success, else the reason the matrix is rejected.
+        std::string build(int32_t n_bits, int32_t n_checks, const int32_t *rp, const int32_t *ci, const int32_t *cp,
+                          const int32_t *ri)
+        {
+            if (n_bits <= 0 || n_checks <= 0 || !rp || !ci || !cp || !ri)
+                return "matrix dimensions must be positive and all four index arrays non-null";
+            n = n_bits;
+            m = n_checks;
+            if (rp[0] != 0 || cp[0] != 0)
+                return "row_ptr[0] and col_ptr[0] must be 0";
+            for (int32_t j = 0; j < m; ++j)
+                if (rp[j + 1] < rp[j])
+                    return "row_ptr is not non-decreasing";
+            for (int32_t i = 0; i < n; ++i)
+                if (cp[i + 1] < cp[i])
+                    return "col_ptr is not non-decreasing";
+            if (rp[m] != cp[n])
+                return "the two adjacency halves hold different numbers of edges (" + std::to_string(rp[m]) + " vs " +
+                       std::to_string(cp[n]) + ")";
+            e = rp[m];
+            if (e <= 0)
+                return "matrix has no edges";
+            for (int32_t p = 0; p < e; ++p)
+            {
+                if (ci[p] < 0 || ci[p] >= n)
+                    return "bit index out of range in the check half";
+                if (ri[p] < 0 || ri[p] >= m)
+                    return "check index out of range in the bit half";
+            }
+
+            // Replay the reference's arrival counters (qkd_ldpc_algorithm.cpp:228-243): scanning the check half in
+            // order, the message for bit b lands in that bit's next free slot.
+            std::vector<int32_t> arrivals(n, 0);
+            std::vector<int32_t> edge_of_bitslot(e, -1); // bit-side slot -> check-side edge that fills it
+            for (int32_t j = 0; j < m; ++j)
+                for (int32_t p = rp[j]; p < rp[j + 1]; ++p)
+                {
+                    const int32_t b = ci[p];
+                    const int32_t w = cp[b + 1] - cp[b];
+                    if (arrivals[b] >= w)
+                        return "bit " + std::to_string(b) + " receives more messages than its weight " + std::to_string(w) +
+                               " (the reference would write past the end of its row)";
+                    edge_of_bitslot[cp[b] + arrivals[b]++] = p;
+                }
+            for (int32_t i = 0; i < n; ++i)
+                if (arrivals[i] != cp[i + 1] - cp[i])
+                    return "bit " + std::to_string(i) + " receives fewer messages than its weight (the reference would read "
+                           "uninitialised memory)";
+            // ... and the reverse direction (:300-311): the message bit i derives from its a-th arrival goes to check
+            // bit_nodes[i][a] and lands in that check's next free slot. The in-place message array requires it to land
+            // exactly on the edge it came from, i.e. both halves list the same edges in a mutually consistent order
+            // (true for the reference's dense loader by construction and for sorted alist files).
+            std::vector<int32_t> carrivals(m, 0);
+            for (int32_t i = 0; i < n; ++i)
+                for (int32_t q = cp[i]; q < cp[i + 1]; ++q)
+                {
+                    const int32_t c = ri[q];
+                    const int32_t w = rp[c + 1] - rp[c];
+                    if (carrivals[c] >= w)
+                        return "check " + std::to_string(c) + " receives more messages than its weight";
+                    const int32_t landing = rp[c] + carrivals[c]++;
+                    if (landing != edge_of_bitslot[q])
+                        return "the bit half and the check half of the matrix are not mutually consistent at bit " +
+                               std::to_string(i) + " (unsorted adjacency lists or different edge sets): the reference's "
+                               "positional routing would misroute messages on this input";
+                }
+
+            row_ptr.assign(rp, rp + m + 1);
+            col_idx.assign(ci, ci + e);
+            words_n = (n + 31) / 32;
+            words_m = (m + 31) / 32;
+            max_check_w = max_bit_w = 0;
+            for (int32_t j = 0; j < m; ++j)
+                max_check_w = std::max(max_check_w, rp[j + 1] - rp[j]);
+            for (int32_t i = 0; i < n; ++i)
+                max_bit_w = std::max(max_bit_w, cp[i + 1] - cp[i]);
+            if (max_check_w > kMaxCheckWeight)
+                return "check weight " + std::to_string(max_check_w) + " exceeds the supported maximum " +
+                       std::to_string(kMaxCheckWeight);
+
+            check_order.resize(m);
+            std::iota(check_order.begin(), check_order.end(), 0u);
+            std::stable_sort(check_order.begin(), check_order.end(), [&](uint32_t a, uint32_t b)
+                             { return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]); });
+            check_pos.resize(m);
+            for (int32_t p = 0; p < m; ++p)
+                check_pos[check_order[p]] = static_cast<uint32_t>(p);
+            cnt.assign(max_check_w, 0);
+            base.assign(max_check_w, 0);
+            for (int32_t j = 0; j < m; ++j)
+                for (int32_t k = 0; k < rp[j + 1] - rp[j]; ++k)
+                    ++cnt[k];
+            for (int32_t k = 1; k < max_check_w; ++k)
+                base[k] = base[k - 1] + cnt[k - 1];
+
+            slot_of_edge.resize(e);
+            col_of_slot.resize(e);
+            for (int32_t j = 0; j < m; ++j)
+                for (int32_t p = rp[j]; p < rp[j + 1]; ++p)
+                {
+                    const uint32_t s = base[p - rp[j]] + check_pos[j];
+                    slot_of_edge[p] = s;
+                    col_of_slot[s] = static_cast<uint32_t>(ci[p]);
+                }
+            bit_slots.assign(static_cast<size_t>(max_bit_w) * n, kNoSlot);
+            for (int32_t i = 0; i < n; ++i)
+                for (int32_t q = cp[i]; q < cp[i + 1]; ++q)
+                    bit_slots[static_cast<size_t>(q - cp[i]) * n + i] = slot_of_edge[edge_of_bitslot[q]];
+            return std::string();
+        }
+    };
+}
