@@ -3,6 +3,7 @@
 // entry that does work launches the sm_100a kernels in qlb_kernels.cuh or fails.
 #include "../../include/qkd_ldpc_b200.h"
 #include "qlb_kernels.cuh"
+#include "qlb_resident_f32.cuh"
 #include "qlb_layout.hpp"
 
 #include <atomic>
@@ -132,6 +133,9 @@ namespace
             d.cnt[k] = k < L.max_check_w ? L.cnt[k] : 0;
             d.base[k] = k < L.max_check_w ? L.base[k] : 0;
         }
+        for (int k = 0; k < 16; ++k)
+            d.base4[k] = 4u * d.base[k];
+        d.uniform_bit_w = L.uniform_bit_w;
         int rc;
         const void *p = nullptr;
         if (L.e < 65535)
@@ -216,6 +220,44 @@ namespace
         return launch_one<Math, kTier, kReconcile, 0, kThreads>(ctx, args);
     }
 
+    // The specialised fp32 kernel (qlb_resident_f32.cuh): whole frame in shared memory, uniform bit weight.
+    template <typename Rule, bool kReconcile, int kBW>
+    int launch_resident(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        constexpr int kThreads = 1024;
+        auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kThreads>;
+        const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.e, kBW);
+        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long grid = ctx->sm_count; // one resident CTA per SM
+        if (grid > args.n_frames)
+            grid = args.n_frames;
+        QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+        args.queue = ctx->d_counters;
+        args.iter_total = ctx->d_counters + 1;
+        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(args);
+        QLB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+        return QLB_OK;
+    }
+
+    template <typename Rule, bool kReconcile>
+    int launch_resident_bw(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        switch (args.code.uniform_bit_w)
+        {
+        case 2: return launch_resident<Rule, kReconcile, 2>(ctx, args);
+        case 3: return launch_resident<Rule, kReconcile, 3>(ctx, args);
+        case 4: return launch_resident<Rule, kReconcile, 4>(ctx, args);
+        default: return fail(QLB_ERR_UNSUPPORTED, "resident kernel: unsupported bit weight");
+        }
+    }
+
+    bool resident_eligible(const qlb_ctx *ctx, const CodeDev &c)
+    {
+        return c.e < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
+               resident_smem_bytes(c.n, c.m, c.e, c.uniform_bit_w) <= (size_t)ctx->smem_optin;
+    }
+
     template <typename Math, bool kReconcile>
     int launch_tier(qlb_ctx *ctx, DecodeArgs &args, int forced_tier)
     {
@@ -248,6 +290,12 @@ namespace
         args.enable_thr = p->enable_threshold;
         args.thr = p->threshold;
         const int forced = (p->flags >> 8) & 0xF ? ((p->flags >> 8) & 0xF) - 1 : -1; // bits 8..11: test hook, tier+1
+        if (p->precision == QLB_PRECISION_F32 && forced < 0 && resident_eligible(ctx, args.code))
+        {
+            if (p->flags & QLB_FLAG_F32_FAST_MATH)
+                return launch_resident_bw<RuleF32Fast, kReconcile>(ctx, args);
+            return launch_resident_bw<RuleF32Accurate, kReconcile>(ctx, args);
+        }
         if (p->precision == QLB_PRECISION_F64)
             return launch_tier<MathF64, kReconcile>(ctx, args, forced);
         if (p->flags & QLB_FLAG_F32_FAST_MATH)

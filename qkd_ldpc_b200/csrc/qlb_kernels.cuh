@@ -36,8 +36,10 @@ namespace qlb
     struct CodeDev
     {
         int32_t n, m, e, words_n, words_m, max_check_w, max_bit_w;
+        int32_t uniform_bit_w; // the common bit weight, or 0 when bits differ in weight
         uint32_t cnt[kMaxCW];  // checks with weight > k
         uint32_t base[kMaxCW]; // first slot of edge position k
+        uint32_t base4[16];    // 4 * base[k] for the fp32 resident kernel (byte offsets, constant-bank operands)
         const uint16_t *bit_slots16; // [max_bit_w][n] (0xFFFF = none), valid when e < 65535
         const uint32_t *bit_slots32; // [max_bit_w][n] (0xFFFFFFFF = none)
         const uint32_t *check_order; // [m]

@@ -32,6 +32,7 @@ namespace qlb
     {
         int32_t n = 0, m = 0, e = 0;
         int32_t max_check_w = 0, max_bit_w = 0;
+        int32_t uniform_bit_w = 0; // common bit weight, 0 when bits differ
         int32_t words_n = 0, words_m = 0;
         std::vector<int32_t> row_ptr, col_idx;   // check half as given (syndrome kernel)
         std::vector<uint32_t> cnt, base;         // [max_check_w]: checks with weight > k; slot offset of edge position k
@@ -117,6 +118,10 @@ namespace qlb
                 max_check_w = std::max(max_check_w, rp[j + 1] - rp[j]);
             for (int32_t i = 0; i < n; ++i)
                 max_bit_w = std::max(max_bit_w, cp[i + 1] - cp[i]);
+            uniform_bit_w = max_bit_w;
+            for (int32_t i = 0; i < n; ++i)
+                if (cp[i + 1] - cp[i] != max_bit_w)
+                    uniform_bit_w = 0;
             if (max_check_w > kMaxCheckWeight)
                 return "check weight " + std::to_string(max_check_w) + " exceeds the supported maximum " +
                        std::to_string(kMaxCheckWeight);
