@@ -53,7 +53,10 @@ enum {
 
 /* qlb_decode_params.flags */
 enum {
-    QLB_FLAG_F32_FAST_MATH = 1 /* fp32 only: exp-domain check rule on MUFU ex2/lg2/rcp instead of tanhf/atanhf */
+    QLB_FLAG_F32_FAST_MATH = 1, /* fp32 only: exp-domain check rule on MUFU ex2/lg2/rcp instead of tanhf/atanhf */
+    /* test hook, bits 8..11 = 1 + storage tier (0 shared memory, 1 L2 scratch for messages, 2 all global): run the generic
+     * kernel in that tier instead of the fastest eligible one; ignored when the tier does not fit */
+    QLB_FLAG_TEST_TIER_SHIFT = 8
 };
 
 typedef struct qlb_code qlb_code; /* a parity-check matrix prepared for the device (replaces H_matrix on the device side) */
@@ -98,7 +101,7 @@ int32_t qlb_code_words_n(const qlb_code *code); /* uint32 words per packed key  
 int32_t qlb_code_words_m(const qlb_code *code); /* uint32 words per packed syndrome = ceil(m/32) */
 
 /* Test/inspection hook: copies the device layout tables into caller buffers (any may be NULL).
- *   slot_of_edge[e]  physical message slot of check-side edge e (CSR position)
+ *   slot_of_edge[e]  physical message slot (< qlb_code_slots()) of check-side edge e (CSR position)
  *   bit_slots[a*n+i] physical slot of the a-th message of bit i in the reference's summation order
  *                    (0xFFFFFFFF when a >= weight of bit i); a < qlb_code_max_bit_weight()
  *   check_order[p]   original check index handled at sorted position p
@@ -107,6 +110,9 @@ int32_t qlb_code_max_bit_weight(const qlb_code *code);
 int32_t qlb_code_max_check_weight(const qlb_code *code);
 int32_t qlb_code_slots(const qlb_code *code);
 int qlb_code_layout(const qlb_code *code, uint32_t *slot_of_edge, uint32_t *bit_slots, uint32_t *check_order);
+/* Mean shared-memory wavefronts per warp-wide message gather of the bit pass (1.0 = conflict free): for the checks in
+ * plain sorted order, and after the bank-aware placement the layout actually uses. */
+int qlb_code_gather_wavefronts(const qlb_code *code, double *naive_out, double *placed_out);
 
 /* ---- context ---------------------------------------------------------------------------------- */
 int qlb_ctx_create(int device, qlb_ctx **ctx_out);

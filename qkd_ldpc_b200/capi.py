@@ -22,6 +22,7 @@ EXPORTS = [
     "qlb_version", "qlb_last_error", "qlb_device_count",
     "qlb_code_create", "qlb_code_destroy", "qlb_code_n", "qlb_code_m", "qlb_code_edges", "qlb_code_words_n",
     "qlb_code_words_m", "qlb_code_max_bit_weight", "qlb_code_max_check_weight", "qlb_code_slots", "qlb_code_layout",
+    "qlb_code_gather_wavefronts",
     "qlb_ctx_create", "qlb_ctx_destroy", "qlb_ctx_device", "qlb_ctx_sm_count", "qlb_ctx_stream", "qlb_ctx_synchronize",
     "qlb_ctx_counters", "qlb_ctx_timer_start", "qlb_ctx_timer_stop",
     "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch",
@@ -70,6 +71,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         getattr(lib, f).argtypes = [vp]
         getattr(lib, f).restype = i32
     lib.qlb_code_layout.argtypes = [vp, vp, vp, vp]
+    lib.qlb_code_gather_wavefronts.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.qlb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.qlb_ctx_destroy.argtypes = [vp]
     lib.qlb_ctx_destroy.restype = None
@@ -146,6 +148,7 @@ class Code:
         self.words_n, self.words_m = self.lib.qlb_code_words_n(h), self.lib.qlb_code_words_m(h)
         self.max_bit_w = self.lib.qlb_code_max_bit_weight(h)
         self.max_check_w = self.lib.qlb_code_max_check_weight(h)
+        self.slots = self.lib.qlb_code_slots(h)
 
     @classmethod
     def from_graph(cls, g, lib=None):
@@ -158,6 +161,11 @@ class Code:
         check_order = np.zeros(self.m, np.uint32)
         _check(self.lib, self.lib.qlb_code_layout(self.handle, _ptr(slot_of_edge), _ptr(bit_slots), _ptr(check_order)))
         return slot_of_edge, bit_slots, check_order
+
+    def gather_wavefronts(self):
+        a, b = C.c_double(), C.c_double()
+        _check(self.lib, self.lib.qlb_code_gather_wavefronts(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "handle", None):

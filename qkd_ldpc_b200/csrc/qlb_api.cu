@@ -136,12 +136,13 @@ namespace
         for (int k = 0; k < 16; ++k)
             d.base4[k] = 4u * d.base[k];
         d.uniform_bit_w = L.uniform_bit_w;
+        d.slots = L.slots;
         int rc;
         const void *p = nullptr;
-        if (L.e < 65535)
+        if (L.slots < 65535)
         {
-            std::vector<uint16_t> s16(L.bit_slots.size());
-            for (size_t i = 0; i < s16.size(); ++i)
+            std::vector<uint16_t> s16((L.bit_slots.size() + 7) / 8 * 8, 0xFFFFu); // 16-byte padded for the TMA bulk copy
+            for (size_t i = 0; i < L.bit_slots.size(); ++i)
                 s16[i] = L.bit_slots[i] == kNoSlot ? 0xFFFFu : static_cast<uint16_t>(L.bit_slots[i]);
             if ((rc = upload(s16.data(), s16.size() * 2, dc, &p)))
                 return rc;
@@ -185,7 +186,7 @@ namespace
     {
         typedef typename Math::real Real;
         auto kern = decode_kernel<Math, kTier, kReconcile, kShapeW, kThreads>;
-        const Carve cv = make_carve<Real, kTier>(args.code.n, args.code.m, args.code.e, args.code.max_bit_w);
+        const Carve cv = make_carve<Real, kTier>(args.code.n, args.code.m, args.code.slots, args.code.max_bit_w);
         QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total_smem));
         int per_sm = 0;
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, cv.total_smem));
@@ -224,9 +225,9 @@ namespace
     template <typename Rule, bool kReconcile, int kBW>
     int launch_resident(qlb_ctx *ctx, DecodeArgs &args)
     {
-        constexpr int kThreads = 1024;
+        constexpr int kThreads = kResidentThreads;
         auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kThreads>;
-        const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.e, kBW);
+        const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.slots, kBW);
         QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long grid = ctx->sm_count; // one resident CTA per SM
         if (grid > args.n_frames)
@@ -254,8 +255,9 @@ namespace
 
     bool resident_eligible(const qlb_ctx *ctx, const CodeDev &c)
     {
-        return c.e < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
-               resident_smem_bytes(c.n, c.m, c.e, c.uniform_bit_w) <= (size_t)ctx->smem_optin;
+        return c.slots < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
+               c.n <= 32 * kResidentThreads && c.m <= 32 * kResidentThreads &&
+               resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) <= (size_t)ctx->smem_optin;
     }
 
     template <typename Math, bool kReconcile>
@@ -263,9 +265,9 @@ namespace
     {
         typedef typename Math::real Real;
         const CodeDev &c = args.code;
-        const bool idx16 = c.e < 65535 && c.bit_slots16 != nullptr;
-        const size_t all = make_carve<Real, kTierSmemAll>(c.n, c.m, c.e, c.max_bit_w).total_smem;
-        const size_t idx = make_carve<Real, kTierSmemIdx>(c.n, c.m, c.e, c.max_bit_w).total_smem;
+        const bool idx16 = c.slots < 65535 && c.bit_slots16 != nullptr;
+        const size_t all = make_carve<Real, kTierSmemAll>(c.n, c.m, c.slots, c.max_bit_w).total_smem;
+        const size_t idx = make_carve<Real, kTierSmemIdx>(c.n, c.m, c.slots, c.max_bit_w).total_smem;
         int tier = kTierGlobal;
         if (idx16 && idx <= (size_t)ctx->smem_optin)
             tier = kTierSmemIdx;
@@ -289,6 +291,7 @@ namespace
         args.max_it = p->max_iterations;
         args.enable_thr = p->enable_threshold;
         args.thr = p->threshold;
+        args.cap_f32 = p->enable_threshold ? (float)p->threshold : INFINITY;
         const int forced = (p->flags >> 8) & 0xF ? ((p->flags >> 8) & 0xF) - 1 : -1; // bits 8..11: test hook, tier+1
         if (p->precision == QLB_PRECISION_F32 && forced < 0 && resident_eligible(ctx, args.code))
         {
@@ -389,7 +392,7 @@ extern "C"
     int32_t qlb_code_words_m(const qlb_code *c) { return c ? c->L.words_m : 0; }
     int32_t qlb_code_max_bit_weight(const qlb_code *c) { return c ? c->L.max_bit_w : 0; }
     int32_t qlb_code_max_check_weight(const qlb_code *c) { return c ? c->L.max_check_w : 0; }
-    int32_t qlb_code_slots(const qlb_code *c) { return c ? c->L.e : 0; }
+    int32_t qlb_code_slots(const qlb_code *c) { return c ? c->L.slots : 0; }
     int qlb_code_layout(const qlb_code *c, uint32_t *slot_of_edge, uint32_t *bit_slots, uint32_t *check_order)
     {
         if (!c)
@@ -400,6 +403,17 @@ extern "C"
             std::memcpy(bit_slots, c->L.bit_slots.data(), c->L.bit_slots.size() * 4);
         if (check_order)
             std::memcpy(check_order, c->L.check_order.data(), c->L.check_order.size() * 4);
+        return QLB_OK;
+    }
+
+    int qlb_code_gather_wavefronts(const qlb_code *c, double *naive_out, double *placed_out)
+    {
+        if (!c)
+            return fail(QLB_ERR_INVALID, "code is null");
+        if (naive_out)
+            *naive_out = c->L.gather_wavefronts_naive;
+        if (placed_out)
+            *placed_out = c->L.gather_wavefronts_opt;
         return QLB_OK;
     }
 

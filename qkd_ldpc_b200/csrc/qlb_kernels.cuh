@@ -37,6 +37,7 @@ namespace qlb
     {
         int32_t n, m, e, words_n, words_m, max_check_w, max_bit_w;
         int32_t uniform_bit_w; // the common bit weight, or 0 when bits differ in weight
+        int32_t slots;         // physical message slots (>= e; rows of slots are 32-aligned)
         uint32_t cnt[kMaxCW];  // checks with weight > k
         uint32_t base[kMaxCW]; // first slot of edge position k
         uint32_t base4[16];    // 4 * base[k] for the fp32 resident kernel (byte offsets, constant-bank operands)
@@ -53,6 +54,7 @@ namespace qlb
         long long n_frames;
         int32_t max_it;
         int32_t enable_thr;
+        float cap_f32; // (float)thr, or +inf when the clamp is disabled
         double thr;
         // reconcile mode
         const uint32_t *alice;    // [F][words_n]
@@ -304,7 +306,7 @@ namespace qlb
         const int n = code.n, m = code.m, tid = threadIdx.x;
         const int words_n = code.words_n, words_m = code.words_m;
         const int max_cw = code.max_check_w, max_bw = code.max_bit_w;
-        const Carve cv = make_carve<Real, kTier>(n, m, code.e, max_bw);
+        const Carve cv = make_carve<Real, kTier>(n, m, code.slots, max_bw);
         unsigned char *scratch = args.scratch + (size_t)blockIdx.x * args.scratch_stride;
 
         Real *msg = reinterpret_cast<Real *>((kTier == kTierSmemAll ? smem : scratch) + cv.msg);

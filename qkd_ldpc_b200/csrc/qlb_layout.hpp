@@ -18,7 +18,9 @@
 // bit reads and overwrites only the slots of its own edges.
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -33,6 +35,8 @@ namespace qlb
         int32_t n = 0, m = 0, e = 0;
         int32_t max_check_w = 0, max_bit_w = 0;
         int32_t uniform_bit_w = 0; // common bit weight, 0 when bits differ
+        int32_t slots = 0;         // physical message slots (>= e: every edge-position row starts on a 32-slot boundary)
+        double gather_wavefronts_naive = 0, gather_wavefronts_opt = 0; // mean shared-memory wavefronts per bit-pass gather
         int32_t words_n = 0, words_m = 0;
         std::vector<int32_t> row_ptr, col_idx;   // check half as given (syndrome kernel)
         std::vector<uint32_t> cnt, base;         // [max_check_w]: checks with weight > k; slot offset of edge position k
@@ -41,6 +45,172 @@ namespace qlb
         std::vector<uint32_t> slot_of_edge;      // [e] physical slot of CSR position
         std::vector<uint32_t> bit_slots;         // [max_bit_w * n], kNoSlot padded
         std::vector<uint32_t> col_of_slot;       // [e] bit index of the edge stored at a slot
+
+        // Bank-aware placement. In the bit pass the 32 lanes of a warp (32 consecutive bits) gather one message each
+        // through bit_slots[a][.]; with rows aligned to 32 slots the bank of a message is its check's sorted position mod
+        // 32. A random placement costs ~3.3 wavefronts per gather (balls in bins); re-ordering the checks inside each
+        // weight class so that the checks met by one warp at one list position fall into distinct banks brings that close
+        // to 1. Greedy placement followed by pairwise swaps that reduce sum(count^2) over (warp, position, bank).
+        void spread_banks(const int32_t *rp, const int32_t *ci, const int32_t *cp, const std::vector<int32_t> &edge_of_bitslot)
+        {
+            const int32_t warps = (n + 31) / 32;
+            const int32_t groups = warps * max_bit_w;
+            if (m < 64 || groups <= 0)
+                return;
+            // groups a check belongs to (one per edge): (warp of the bit, position of this edge in the bit's list)
+            std::vector<std::vector<int32_t>> groups_of(m);
+            for (int32_t i = 0; i < n; ++i)
+                for (int32_t q = cp[i]; q < cp[i + 1]; ++q)
+                {
+                    const int32_t edge = edge_of_bitslot[q];
+                    const int32_t j = static_cast<int32_t>(std::upper_bound(rp, rp + m + 1, edge) - rp) - 1;
+                    groups_of[j].push_back((i / 32) * max_bit_w + (q - cp[i]));
+                }
+            (void)ci;
+            std::vector<uint8_t> count(static_cast<size_t>(groups) * 32, 0);
+            auto true_cost = [&](const std::vector<int32_t> &bank)
+            {
+                std::vector<uint8_t> c(static_cast<size_t>(groups) * 32, 0);
+                for (int32_t j = 0; j < m; ++j)
+                    for (int32_t g : groups_of[j])
+                        ++c[static_cast<size_t>(g) * 32 + bank[j]];
+                double tot = 0;
+                int64_t used = 0;
+                for (int32_t g = 0; g < groups; ++g)
+                {
+                    int mx = 0;
+                    for (int b = 0; b < 32; ++b)
+                        mx = std::max<int>(mx, c[static_cast<size_t>(g) * 32 + b]);
+                    if (mx > 0)
+                    {
+                        tot += mx;
+                        ++used;
+                    }
+                }
+                if (std::getenv("QLB_BANK_DEBUG"))
+                {
+                    long hist[8] = {0}, pairs = 0;
+                    for (int32_t g = 0; g < groups; ++g)
+                    {
+                        int mx = 0;
+                        for (int b = 0; b < 32; ++b)
+                        {
+                            const int v = c[static_cast<size_t>(g) * 32 + b];
+                            mx = std::max(mx, v);
+                            pairs += v * (v - 1) / 2;
+                        }
+                        ++hist[std::min(mx, 7)];
+                    }
+                    std::fprintf(stderr, "bank placement: groups by max multiplicity 1:%ld 2:%ld 3:%ld 4:%ld 5+:%ld colliding pairs %ld\n",
+                                 hist[1], hist[2], hist[3], hist[4], hist[5] + hist[6] + hist[7], pairs);
+                }
+                return used ? tot / static_cast<double>(used) : 0.0;
+            };
+            // weight classes are contiguous runs of sorted positions
+            std::vector<int32_t> bank(m, 0);
+            {
+                std::vector<int32_t> naive(m);
+                for (int32_t p = 0; p < m; ++p)
+                    naive[check_order[p]] = p % 32;
+                gather_wavefronts_naive = true_cost(naive);
+            }
+            uint64_t rng = 0x9E3779B97F4A7C15ull;
+            auto next = [&]()
+            {
+                rng ^= rng << 13;
+                rng ^= rng >> 7;
+                rng ^= rng << 17;
+                return rng;
+            };
+            int32_t lo = 0;
+            std::vector<uint32_t> new_order(m);
+            while (lo < m)
+            {
+                int32_t hi = lo;
+                const int32_t w = rp[check_order[lo] + 1] - rp[check_order[lo]];
+                while (hi < m && rp[check_order[hi] + 1] - rp[check_order[hi]] == w)
+                    ++hi;
+                std::vector<int32_t> cap(32, 0);
+                for (int32_t p = lo; p < hi; ++p)
+                    ++cap[p % 32];
+                std::vector<int32_t> members(check_order.begin() + lo, check_order.begin() + hi);
+                // greedy
+                for (int32_t j : members)
+                {
+                    int best = -1;
+                    long best_cost = 0;
+                    for (int b = 0; b < 32; ++b)
+                    {
+                        if (cap[b] == 0)
+                            continue;
+                        long c = 0;
+                        for (int32_t g : groups_of[j])
+                            c += count[static_cast<size_t>(g) * 32 + b];
+                        if (best < 0 || c < best_cost)
+                        {
+                            best = b;
+                            best_cost = c;
+                        }
+                    }
+                    bank[j] = best;
+                    --cap[best];
+                    for (int32_t g : groups_of[j])
+                        ++count[static_cast<size_t>(g) * 32 + best];
+                }
+                // pairwise swaps
+                const size_t sz = members.size();
+                if (sz >= 2)
+                {
+                    auto delta_move = [&](int32_t j, int from, int to)
+                    {
+                        long d = 0;
+                        for (int32_t g : groups_of[j])
+                        {
+                            const long cf = count[static_cast<size_t>(g) * 32 + from], ct = count[static_cast<size_t>(g) * 32 + to];
+                            d += (2 * ct + 1) - (2 * cf - 1); // (ct+1)^2 - ct^2 + (cf-1)^2 - cf^2
+                        }
+                        return d;
+                    };
+                    auto apply_move = [&](int32_t j, int from, int to)
+                    {
+                        for (int32_t g : groups_of[j])
+                        {
+                            --count[static_cast<size_t>(g) * 32 + from];
+                            ++count[static_cast<size_t>(g) * 32 + to];
+                        }
+                        bank[j] = to;
+                    };
+                    const char *env = std::getenv("QLB_BANK_TRIALS");
+                    const size_t trials = sz * (env ? std::strtoul(env, nullptr, 10) : 400);
+                    for (size_t t = 0; t < trials; ++t)
+                    {
+                        const int32_t j1 = members[next() % sz], j2 = members[next() % sz];
+                        const int b1 = bank[j1], b2 = bank[j2];
+                        if (b1 == b2)
+                            continue;
+                        const long d1 = delta_move(j1, b1, b2);
+                        apply_move(j1, b1, b2);
+                        const long d2 = delta_move(j2, b2, b1);
+                        if (d1 + d2 < 0)
+                            apply_move(j2, b2, b1);
+                        else
+                            apply_move(j1, b2, b1); // undo
+                    }
+                }
+                // positions lo..hi-1: position p takes the next check assigned to bank p % 32 (original order inside a bank)
+                std::vector<std::vector<int32_t>> by_bank(32);
+                std::vector<int32_t> sorted_members = members;
+                std::sort(sorted_members.begin(), sorted_members.end());
+                for (int32_t j : sorted_members)
+                    by_bank[bank[j]].push_back(j);
+                std::vector<size_t> taken(32, 0);
+                for (int32_t p = lo; p < hi; ++p)
+                    new_order[p] = static_cast<uint32_t>(by_bank[p % 32][taken[p % 32]++]);
+                lo = hi;
+            }
+            check_order = new_order;
+            gather_wavefronts_opt = true_cost(bank);
+        }
 
         // Returns an empty string on success, else the reason the matrix is rejected.
         std::string build(int32_t n_bits, int32_t n_checks, const int32_t *rp, const int32_t *ci, const int32_t *cp,
@@ -130,6 +300,7 @@ namespace qlb
             std::iota(check_order.begin(), check_order.end(), 0u);
             std::stable_sort(check_order.begin(), check_order.end(), [&](uint32_t a, uint32_t b)
                              { return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]); });
+            spread_banks(rp, ci, cp, edge_of_bitslot);
             check_pos.resize(m);
             for (int32_t p = 0; p < m; ++p)
                 check_pos[check_order[p]] = static_cast<uint32_t>(p);
@@ -138,11 +309,13 @@ namespace qlb
             for (int32_t j = 0; j < m; ++j)
                 for (int32_t k = 0; k < rp[j + 1] - rp[j]; ++k)
                     ++cnt[k];
+            // every row of slots starts on a multiple of 32, so the shared-memory bank of a slot is (sorted position % 32)
             for (int32_t k = 1; k < max_check_w; ++k)
-                base[k] = base[k - 1] + cnt[k - 1];
+                base[k] = base[k - 1] + (cnt[k - 1] + 31u) / 32u * 32u;
+            slots = static_cast<int32_t>(base[max_check_w - 1] + cnt[max_check_w - 1]);
 
             slot_of_edge.resize(e);
-            col_of_slot.resize(e);
+            col_of_slot.assign(slots, kNoSlot);
             for (int32_t j = 0; j < m; ++j)
                 for (int32_t p = rp[j]; p < rp[j + 1]; ++p)
                 {

@@ -3,14 +3,17 @@
 // 60 KB of slot indices). Same schedule and node arithmetic as decode_kernel (qlb_kernels.cuh), re-organised so that
 // the inner loops carry (almost) nothing but the node arithmetic:
 //
-//   * a warp's checks all have the same weight (checks are sorted by weight), so the check update is dispatched once
-//     per check to code fully unrolled for that weight -- no per-edge predicates, no local arrays;
+//   * checks are sorted by weight, so the check pass runs weight segment by weight segment through code fully unrolled
+//     for that weight -- no per-edge predicates, no local arrays, no per-check dispatch;
 //   * the hard decision z of a bit travels in the least-significant mantissa bit of the bit-to-check messages that bit
 //     sends (a <= 1 ulp perturbation; fp32 has no bit-exactness contract, its bar is statistical). The check pass
 //     XORs the raw words it loads anyway: bit 31 of the XOR is the product's sign, bit 0 is the check's parity. The
 //     separate parity phase, its barrier, and the per-edge byte array of decode_kernel disappear;
 //   * convergence of iteration t is therefore seen by the check pass of iteration t+1 (one speculative check pass per
 //     successful frame, < 1 % of the sweep's work, against ~20 % saved in every iteration);
+//   * a thread visits the same checks and bits in every iteration, so their syndrome bits and prior signs are packed
+//     once per frame into two registers;
+//   * the bit->slot table is staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier) per CTA;
 //   * two block barriers per iteration.
 //
 // Reference semantics restated (paths relative to the reference repository): src/qkd_ldpc_algorithm.cpp:175-345, 398-447;
@@ -40,14 +43,41 @@ namespace qlb
         return y;
     }
 
-    // Check rules for a check of weight exactly W. v[] holds the raw incoming messages and receives the outgoing ones.
-    // `xr` is the XOR of the raw message words with the syndrome bit folded into bit 31 (sign of the seeded product).
+    // ---- TMA bulk copy global -> shared, completion on an mbarrier ---------------------------------------------------
+    __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+    __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+    {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                     "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
+    }
+    __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                     "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+                     "r"(parity)
+                     : "memory");
+    }
+
+    // ---- check rules for a check of weight exactly W -------------------------------------------------------------------
+    // v[] holds the raw incoming messages and receives the outgoing ones. xr = XOR of the raw message words, with the
+    // check's syndrome bit folded into bit 31 (sign of the seeded product, src/qkd_ldpc_algorithm.cpp:231).
     struct RuleF32Fast
     {
         // v = exp(-|m|): tanh(|m|/2) = (1-v)/(1+v); leave-one-out products A_k = prod(1-v), B_k = prod(1+v);
-        // 2 atanh(A_k/B_k) = ln((B_k+A_k)/(B_k-A_k)). One MUFU.EX2 + MUFU.RCP + MUFU.LG2 per edge.
+        // 2 atanh(A_k/B_k) = ln((B_k+A_k)/(B_k-A_k)). One MUFU.EX2 + MUFU.RCP + MUFU.LG2 per edge; signs by XOR.
         template <int W>
-        static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, uint32_t sbit, float cap)
+        static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, float cap)
         {
             float a[W], b[W], preA[W], preB[W];
             float runA = 1.f, runB = 1.f;
@@ -67,12 +97,11 @@ namespace qlb
             for (int k = W - 1; k >= 0; --k)
             {
                 const float Ak = preA[k] * sufA, Bk = preB[k] * sufB;
-                const uint32_t sk = (xr ^ __float_as_uint(v[k])) & 0x80000000u;
                 float mag = 0.6931471805599453f * lg2_approx((Bk + Ak) * rcp_approx(Bk - Ak));
                 mag = fminf(mag, cap); // +inf (saturated product) -> threshold; the clamp of :246-249
-                v[k] = __uint_as_float(__float_as_uint(mag) | sk);
                 sufA *= a[k];
                 sufB *= b[k];
+                v[k] = __uint_as_float(((xr ^ __float_as_uint(v[k])) & 0x80000000u) | __float_as_uint(mag));
             }
         }
     };
@@ -81,10 +110,14 @@ namespace qlb
     {
         // libdevice tanhf / atanhf, leave-one-out product by prefix * suffix
         template <int W>
-        static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, uint32_t sbit, float cap)
+        static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, float cap)
         {
             float t[W], pre[W];
-            float run = sbit ? -1.f : 1.f;
+            uint32_t sx = xr; // bit 31: syndrome ^ all message signs; strip the message signs to get the seed's sign
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                sx ^= __float_as_uint(v[k]);
+            float run = (sx & 0x80000000u) ? -1.f : 1.f;
 #pragma unroll
             for (int k = 0; k < W; ++k)
             {
@@ -104,50 +137,68 @@ namespace qlb
         }
     };
 
-    // One check of weight exactly W at sorted position p. base4[k] (kernel parameter => constant bank, compile-time k)
-    // is the byte offset of edge position k's slot row; p4 = 4 * p.
-    template <typename Rule, int W>
-    __device__ __forceinline__ uint32_t check_fixed(unsigned char *__restrict__ msg_bytes, const DecodeArgs &args, uint32_t p4,
-                                                    uint32_t sbit, float cap)
+    // Where the byte offset of edge position k's slot row comes from: the kernel parameters (constant bank, a free operand
+    // for compile-time k) on the hot path, a shared-memory copy for the out-of-line wide weights.
+    struct BaseFromParams
     {
-        float v[W];
-        uint32_t xr = sbit << 31;
-#pragma unroll
-        for (int k = 0; k < W; ++k)
+        const DecodeArgs &args;
+        __device__ __forceinline__ uint32_t operator()(int k) const { return args.code.base4[k]; }
+    };
+    struct BaseFromSmem
+    {
+        const uint32_t *base4;
+        __device__ __forceinline__ uint32_t operator()(int k) const { return base4[k]; }
+    };
+
+    // All checks of weight exactly W: sorted positions [lo, hi). Round r of the thread's walk uses bit `rbit` of my_syn.
+    // Returns the OR over the thread's checks of (parity of the riding hard decisions) ^ (syndrome bit), in bit 0.
+    template <typename Rule, int W, int kThreads, typename Base>
+    __device__ __forceinline__ uint32_t check_segment(unsigned char *__restrict__ msg_bytes, const Base base4, uint32_t lo, uint32_t hi,
+                                                      uint32_t my_syn, int &rbit, float cap)
+    {
+        uint32_t bad = 0;
+#pragma unroll 1
+        for (uint32_t p = lo + threadIdx.x; p < hi; p += kThreads, ++rbit)
         {
-            v[k] = *reinterpret_cast<const float *>(msg_bytes + (args.code.base4[k] + p4));
-            xr ^= __float_as_uint(v[k]);
-        }
-        Rule::template apply<W>(v, xr, sbit, cap);
+            const uint32_t sb = (my_syn >> rbit) & 1u;
+            uint32_t xr = sb * 0x80000001u; // bit 31: sign seed, bit 0: parity seed
+            const uint32_t p4 = 4u * p;
+            float v[W];
 #pragma unroll
-        for (int k = 0; k < W; ++k)
-            *reinterpret_cast<float *>(msg_bytes + (args.code.base4[k] + p4)) = v[k];
-        return (xr ^ sbit) & 1u; // parity of the hard decisions riding in bit 0, against the syndrome bit
+            for (int k = 0; k < W; ++k)
+            {
+                v[k] = *reinterpret_cast<const float *>(msg_bytes + (base4(k) + p4));
+                xr ^= __float_as_uint(v[k]);
+            }
+            bad |= xr;
+            Rule::template apply<W>(v, xr, cap);
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                *reinterpret_cast<float *>(msg_bytes + (base4(k) + p4)) = v[k];
+        }
+        return bad;
     }
 
-    template <typename Rule>
-    __device__ __forceinline__ uint32_t check_any(unsigned char *__restrict__ msg_bytes, const DecodeArgs &args, uint32_t p4, int w,
-                                                  uint32_t sbit, float cap)
+    // weights 9..16 are kept out of line: their register appetite must not leak into the hot (narrow) instantiations
+    template <typename Rule, int W, int kThreads>
+    __device__ __noinline__ uint32_t check_segment_wide(unsigned char *msg_bytes, const uint32_t *s_base4, uint32_t lo, uint32_t hi,
+                                                        uint32_t my_syn, int rbit, float cap)
     {
-        switch (w)
-        {
-#define QLB_CASE(W_) case W_: return check_fixed<Rule, W_>(msg_bytes, args, p4, sbit, cap);
-            QLB_CASE(1) QLB_CASE(2) QLB_CASE(3) QLB_CASE(4) QLB_CASE(5) QLB_CASE(6) QLB_CASE(7) QLB_CASE(8)
-            QLB_CASE(9) QLB_CASE(10) QLB_CASE(11) QLB_CASE(12) QLB_CASE(13) QLB_CASE(14) QLB_CASE(15) QLB_CASE(16)
-#undef QLB_CASE
-        default: return 0;
-        }
+        const uint32_t bad = check_segment<Rule, W, kThreads>(msg_bytes, BaseFromSmem{s_base4}, lo, hi, my_syn, rbit, cap);
+        return (bad & 1u) | ((uint32_t)rbit << 1); // bit 0: parity failure, bits 1..: advanced round counter
     }
 
     constexpr int kResidentMaxCW = 16;
+    constexpr int kResidentThreads = 1024;
 
-    __host__ __device__ inline size_t resident_smem_bytes(int n, int m, int e, int bw)
+    __host__ __device__ inline size_t resident_smem_bytes(int n, int m, int slots, int bw)
     {
         const size_t wn = align_up((size_t)(n + 31) / 32 * 4, 16), wm = align_up((size_t)(m + 31) / 32 * 4, 16);
-        return align_up((size_t)e * 4, 16) + align_up((size_t)bw * n * 2, 16) + 3 * wn + 2 * wm + 256;
+        return align_up((size_t)slots * 4, 16) + align_up((size_t)bw * n * 2, 16) + 3 * wn + wm + 256;
     }
 
-    // kBW: the (uniform) bit weight. Requirements checked by the host: e < 65535, max_check_w <= 16, every bit of weight kBW.
+    // kBW: the (uniform) bit weight. Host-checked requirements: slots < 65535, max_check_w <= 16, every bit of weight kBW,
+    // m <= 32 * kThreads and n <= 32 * kThreads (one register bit per visited node).
     template <typename Rule, bool kReconcile, int kBW, int kThreads>
     __global__ void __launch_bounds__(kThreads, 1) decode_resident_f32_kernel(const DecodeArgs args)
     {
@@ -156,25 +207,42 @@ namespace qlb
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31;
         const int words_n = code.words_n, words_m = code.words_m;
         const size_t wn = align_up((size_t)words_n * 4, 16), wm = align_up((size_t)words_m * 4, 16);
+        const uint32_t idx_bytes = (uint32_t)align_up((size_t)kBW * n * 2, 16);
 
         float *msg = reinterpret_cast<float *>(smem);
-        uint16_t *bslot = reinterpret_cast<uint16_t *>(smem + align_up((size_t)code.e * 4, 16));
-        unsigned char *tail = reinterpret_cast<unsigned char *>(bslot) + align_up((size_t)kBW * n * 2, 16);
+        unsigned char *msg_bytes = smem;
+        uint16_t *bslot = reinterpret_cast<uint16_t *>(smem + align_up((size_t)code.slots * 4, 16));
+        unsigned char *tail = reinterpret_cast<unsigned char *>(bslot) + idx_bytes;
         uint32_t *s_bob = reinterpret_cast<uint32_t *>(tail);
         uint32_t *s_alice = reinterpret_cast<uint32_t *>(tail + wn);
         uint32_t *s_z = reinterpret_cast<uint32_t *>(tail + 2 * wn);
-        uint32_t *s_synp = reinterpret_cast<uint32_t *>(tail + 3 * wn);
-        uint32_t *s_synn = reinterpret_cast<uint32_t *>(tail + 3 * wn + wm);
-        uint32_t *s_cnt = reinterpret_cast<uint32_t *>(tail + 3 * wn + 2 * wm); // [16]
-        long long *s_frame = reinterpret_cast<long long *>(s_cnt + kResidentMaxCW);
+        uint32_t *s_synn = reinterpret_cast<uint32_t *>(tail + 3 * wn); // syndrome, natural check order
+        uint32_t *s_cnt = reinterpret_cast<uint32_t *>(tail + 3 * wn + wm); // [17]
+        uint32_t *s_base4 = s_cnt + 18;                                       // [16]
+        uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_base4 + 16);
+        long long *s_frame = reinterpret_cast<long long *>(s_bar + 1);
 
-        for (int i = tid; i < kBW * n; i += kThreads)
-            bslot[i] = code.bit_slots16[i];
+        // stage the bit->slot table: one TMA bulk copy per CTA (the table is 16-byte padded on the device)
+        if (tid == 0)
+            mbar_init(s_bar, 1);
+        if (tid <= kResidentMaxCW)
+            s_cnt[tid] = tid < kResidentMaxCW ? code.cnt[tid] : 0;
         if (tid < kResidentMaxCW)
-            s_cnt[tid] = code.cnt[tid];
+            s_base4[tid] = code.base4[tid];
+        __syncthreads();
+        if (tid == 0)
+        {
+            mbar_expect_tx(s_bar, idx_bytes);
+            tma_bulk_g2s(bslot, code.bit_slots16, idx_bytes, s_bar);
+        }
+        mbar_wait(s_bar, 0);
+
         const int wmax = code.max_check_w;
-        const float cap = args.enable_thr ? (float)args.thr : __int_as_float(0x7f800000);
-        const int n_round = (n + 31) & ~31, m_round = (m + 31) & ~31;
+        const float cap = args.cap_f32;
+        const uint16_t *bs[kBW];
+#pragma unroll
+        for (int a = 0; a < kBW; ++a)
+            bs[a] = bslot + a * n;
 
         for (;;)
         {
@@ -209,77 +277,89 @@ namespace qlb
             __syncthreads();
 
             // messages <- priors (src/qkd_ldpc_algorithm.cpp:182-190); in reconcile mode Alice's bit rides in bit 0 so
-            // that the parity of the first pass over the checks is her syndrome (:413-414)
-            for (int i = tid; i < n; i += kThreads)
+            // that the parity of the first walk over the checks is her syndrome (:413-414). my_bob: Bob's bit of the
+            // r-th bit this thread visits.
+            uint32_t my_bob = 0;
             {
-                float prior;
-                uint32_t abit = 0;
-                if (kReconcile)
+                int r = 0;
+                for (int i = tid; i < n; i += kThreads, ++r)
                 {
-                    const uint32_t bb = (s_bob[i >> 5] >> (i & 31)) & 1u;
-                    abit = (s_alice[i >> 5] >> (i & 31)) & 1u;
-                    prior = bb ? -lp : lp;
-                }
-                else
-                    prior = (float)llr_f[i];
-                const float pv = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
-#pragma unroll
-                for (int a = 0; a < kBW; ++a)
-                    msg[bslot[a * n + i]] = pv;
-            }
-            __syncthreads();
-
-            for (int p = tid; p < m_round; p += kThreads)
-            {
-                uint32_t bit = 0;
-                if (p < m)
-                {
+                    float prior;
+                    uint32_t abit = 0;
                     if (kReconcile)
                     {
-                        for (int k = 0; k < wmax; ++k)
-                            if ((uint32_t)p < s_cnt[k])
-                                bit ^= __float_as_uint(msg[code.base[k] + p]);
-                        bit &= 1u;
-                        if (bit)
-                        {
-                            const uint32_t j = code.check_order[p];
-                            atomicOr(&s_synn[j >> 5], 1u << (j & 31));
-                        }
+                        const uint32_t bb = (s_bob[i >> 5] >> lane) & 1u;
+                        abit = (s_alice[i >> 5] >> lane) & 1u;
+                        my_bob |= bb << r;
+                        prior = bb ? -lp : lp;
                     }
                     else
-                    {
-                        const uint32_t j = code.check_order[p];
-                        bit = (s_synn[j >> 5] >> (j & 31)) & 1u;
-                    }
+                        prior = (float)llr_f[i];
+                    const float pv = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
+#pragma unroll
+                    for (int a = 0; a < kBW; ++a)
+                        msg[bs[a][i]] = pv;
                 }
-                const uint32_t word = __ballot_sync(0xffffffffu, bit != 0);
-                if (lane == 0)
-                    s_synp[p >> 5] = word;
             }
             __syncthreads();
 
+            // my_syn: target syndrome bit of the r-th check this thread visits (same walk as the check pass)
+            uint32_t my_syn = 0;
+            {
+                int r = 0;
+                for (int w = wmax; w >= 0; --w)
+                {
+                    const uint32_t lo = (w < wmax) ? s_cnt[w] : 0u, hi = (w > 0) ? s_cnt[w - 1] : (uint32_t)m;
+                    for (uint32_t p = lo + tid; p < hi; p += kThreads, ++r)
+                    {
+                        const uint32_t j = code.check_order[p];
+                        uint32_t bit = 0;
+                        if (kReconcile)
+                        {
+                            for (int k = 0; k < w; ++k)
+                                bit ^= __float_as_uint(msg[code.base[k] + p]);
+                            bit &= 1u;
+                            if (bit && args.syndrome_out)
+                                atomicOr(&s_synn[j >> 5], 1u << (j & 31));
+                        }
+                        else
+                            bit = (s_synn[j >> 5] >> (j & 31)) & 1u;
+                        my_syn |= bit << r;
+                    }
+                }
+            }
+            // (no barrier needed: every thread only re-reads the slots of its own checks next)
+
             // ---- iterations ----------------------------------------------------------------------------------------
-            // Loop index `it` counts completed bit passes. The check pass of round `it` also evaluates the parity of the
-            // hard decisions of bit pass `it` (meaningless for it == 0: bit 0 then still holds Alice's / zero bits).
+            // `it` counts completed bit passes. The check pass of round `it` also evaluates the parity of the hard
+            // decisions of bit pass `it` (meaningless for it == 0: bit 0 then still holds Alice's / zero bits).
             int it = 0;
             bool success = false;
             for (;;)
             {
                 uint32_t bad = 0;
-                int w = wmax;
-                for (int p = tid; p < m; p += kThreads)
+                int rbit = 0;
+#pragma unroll 1
+                for (int w = wmax; w >= 1; --w)
                 {
-                    const uint32_t sbit = (s_synp[p >> 5] >> lane) & 1u;
-                    if ((uint32_t)p >= s_cnt[0])
-                    {
-                        bad |= sbit; // a check without edges can only be satisfied by a zero syndrome bit
+                    const uint32_t lo = (w < wmax) ? s_cnt[w] : 0u, hi = s_cnt[w - 1];
+                    if (lo >= hi)
                         continue;
+                    switch (w)
+                    {
+#define QLB_SEG(W_) case W_: bad |= check_segment<Rule, W_, kThreads>(msg_bytes, BaseFromParams{args}, lo, hi, my_syn, rbit, cap); break;
+#define QLB_SEGW(W_) case W_: { const uint32_t rv = check_segment_wide<Rule, W_, kThreads>(msg_bytes, s_base4, lo, hi, my_syn, rbit, cap); bad |= rv & 1u; rbit = (int)(rv >> 1); } break;
+                        QLB_SEG(1) QLB_SEG(2) QLB_SEG(3) QLB_SEG(4) QLB_SEG(5) QLB_SEG(6) QLB_SEG(7) QLB_SEG(8)
+                        QLB_SEGW(9) QLB_SEGW(10) QLB_SEGW(11) QLB_SEGW(12) QLB_SEGW(13) QLB_SEGW(14) QLB_SEGW(15) QLB_SEGW(16)
+#undef QLB_SEG
+#undef QLB_SEGW
+                    default: break;
                     }
-                    while (w > 1 && (uint32_t)p >= s_cnt[w - 1])
-                        --w;
-                    bad |= check_any<Rule>(reinterpret_cast<unsigned char *>(msg), args, 4u * (uint32_t)p, w, sbit, cap);
                 }
-                const int any_bad = __syncthreads_or((int)bad);
+                // checks without edges can only be satisfied by a zero syndrome bit
+                for (uint32_t p = s_cnt[0] + tid; p < (uint32_t)m; p += kThreads, ++rbit)
+                    bad |= (my_syn >> rbit) & 1u;
+                const int any_bad = __syncthreads_or((int)(bad & 1u));
                 if (it > 0 && !any_bad)
                 {
                     success = true; // the decisions of bit pass `it` satisfy the syndrome (:285-298)
@@ -288,40 +368,42 @@ namespace qlb
                 if (it == args.max_it)
                     break; // :337-344
                 // bit pass: total (:256-258), decision (:259-266), extrinsic + clamp (:300-316)
-                for (int i = tid; i < n_round; i += kThreads)
                 {
-                    bool z = false;
-                    if (i < n)
+                    int r = 0;
+#pragma unroll 1
+                    for (int i = tid; i < n; i += kThreads, ++r)
                     {
                         float prior;
                         if (kReconcile)
-                            prior = ((s_bob[i >> 5] >> lane) & 1u) ? -lp : lp;
+                            prior = __uint_as_float(__float_as_uint(lp) ^ (((my_bob >> r) & 1u) << 31));
                         else
                             prior = (float)llr_f[i];
                         uint32_t sl[kBW];
                         float c[kBW];
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
-                            sl[a] = bslot[a * n + i];
+                            sl[a] = 4u * (uint32_t)bs[a][i];
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
-                            c[a] = msg[sl[a]];
+                            c[a] = *reinterpret_cast<const float *>(msg_bytes + sl[a]);
                         float total = prior;
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
                             total = total + c[a];
-                        z = total <= 0.f;
+                        const bool z = total <= 0.f;
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
                         {
                             float v = total - c[a];
                             v = fminf(fmaxf(v, -cap), cap);
-                            msg[sl[a]] = __uint_as_float((__float_as_uint(v) & ~1u) | (uint32_t)z);
+                            *reinterpret_cast<float *>(msg_bytes + sl[a]) = __uint_as_float((__float_as_uint(v) & ~1u) | (uint32_t)z);
                         }
+                        // lanes of one warp leave this loop together except in the last, partial word of the key
+                        const uint32_t lanes = (i - lane + 32 <= n) ? 0xffffffffu : ((1u << (n & 31)) - 1u);
+                        const uint32_t word = __ballot_sync(lanes, z);
+                        if (lane == 0)
+                            s_z[i >> 5] = word;
                     }
-                    const uint32_t word = __ballot_sync(0xffffffffu, z);
-                    if (lane == 0)
-                        s_z[i >> 5] = word;
                 }
                 ++it;
                 __syncthreads();

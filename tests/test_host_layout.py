@@ -35,7 +35,7 @@ def emulate(code: capi.Code, mat, bob, syn, log_p, max_it=100, thr=100.0, enable
     slot_of_edge, bit_slots, check_order = code.layout()
     n, m = mat.n, mat.m
     none = np.uint32(0xFFFFFFFF)
-    msg = np.zeros(mat.e)
+    msg = np.zeros(code.slots)
     prior = np.where(np.asarray(bob) != 0, -log_p, log_p)
     for a in range(bit_slots.shape[0]):
         ok = bit_slots[a] != none
@@ -87,7 +87,7 @@ def test_layout_emulation_small_codes(matrices, graphs, dev_codes, oracle, name)
 def test_layout_tables_north_star(matrices, dev_codes):
     mat, code = matrices[NS], dev_codes[NS]
     slot_of_edge, bit_slots, check_order = code.layout()
-    assert sorted(slot_of_edge.tolist()) == list(range(mat.e)), "slots must be a permutation of the edges"
+    assert len(set(slot_of_edge.tolist())) == mat.e and slot_of_edge.max() < code.slots, "edges must own distinct slots"
     assert sorted(check_order.tolist()) == list(range(mat.m))
     w = np.diff(mat.row_ptr)[check_order]
     assert (np.diff(w) <= 0).all(), "checks must be sorted by descending weight"
@@ -95,7 +95,9 @@ def test_layout_tables_north_star(matrices, dev_codes):
     pos = np.empty(mat.m, np.int64)
     pos[check_order] = np.arange(mat.m)
     cnt = np.array([(np.diff(mat.row_ptr) > k).sum() for k in range(code.max_check_w)])
-    base = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    base = np.concatenate([[0], np.cumsum((cnt + 31) // 32 * 32)[:-1]])   # rows of slots start on 32-slot boundaries
+    naive, placed = code.gather_wavefronts()
+    assert placed <= 0.7 * naive and placed <= 2.05, (naive, placed)          # bank-aware placement of the checks
     for j in (0, 1, 700, mat.m - 1):
         for k, p in enumerate(range(mat.row_ptr[j], mat.row_ptr[j + 1])):
             assert slot_of_edge[p] == base[k] + pos[j]
