@@ -256,8 +256,8 @@ namespace
     bool resident_eligible(const qlb_ctx *ctx, const CodeDev &c)
     {
         return c.slots < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
-               c.n <= 32 * kResidentThreads && c.m <= 32 * kResidentThreads &&
-               resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) <= (size_t)ctx->smem_optin;
+               c.n <= 32 * kResidentThreads && c.m <= 32 * kResidentThreads && c.n % 32 == 0 &&
+               resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) + kResidentStaticSmem <= (size_t)ctx->smem_optin;
     }
 
     template <typename Math, bool kReconcile>

@@ -74,33 +74,34 @@ namespace qlb
     // check's syndrome bit folded into bit 31 (sign of the seeded product, src/qkd_ldpc_algorithm.cpp:231).
     struct RuleF32Fast
     {
-        // v = exp(-|m|): tanh(|m|/2) = (1-v)/(1+v); leave-one-out products A_k = prod(1-v), B_k = prod(1+v);
-        // 2 atanh(A_k/B_k) = ln((B_k+A_k)/(B_k-A_k)). One MUFU.EX2 + MUFU.RCP + MUFU.LG2 per edge; signs by XOR.
+        // Messages are kept in base-2 units (LLR / ln 2): with e = 2^-|m|, tanh(|m| ln2 / 2) = (1-e)/(1+e). For the whole
+        // check A = prod(1-e_j), B = prod(1+e_j), S = B + A, D = B - A; the leave-one-out ratio of edge k follows without
+        // a division or prefix/suffix products:
+        //     (B_k + A_k) / (B_k - A_k) = (S - e_k D) / (D - e_k S),     out_k = log2 of that, sign by XOR.
+        // One MUFU.EX2 + MUFU.RCP + MUFU.LG2 per edge. The absolute error floor of the denominator (~6e-8) is that of
+        // forming B_k - A_k directly. A denominator rounded to zero gives +inf, one rounded below zero gives NaN out of
+        // lg2; fminf(NaN or +inf, cap) = cap, so both saturate to the clamp exactly like a saturated product (:246-249).
+        static constexpr float kUnit = 1.4426950408889634f; // messages = LLR * kUnit
         template <int W>
         static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, float cap)
         {
-            float a[W], b[W], preA[W], preB[W];
-            float runA = 1.f, runB = 1.f;
+            float e[W];
+            float A = 1.f, B = 1.f;
 #pragma unroll
             for (int k = 0; k < W; ++k)
             {
-                const float e = ex2_approx(-1.4426950408889634f * fabsf(v[k]));
-                a[k] = 1.f - e;
-                b[k] = 1.f + e;
-                preA[k] = runA;
-                preB[k] = runB;
-                runA *= a[k];
-                runB *= b[k];
+                e[k] = ex2_approx(-fabsf(v[k]));
+                A *= 1.f - e[k];
+                B *= 1.f + e[k];
             }
-            float sufA = 1.f, sufB = 1.f;
+            const float S = B + A, D = B - A;
 #pragma unroll
-            for (int k = W - 1; k >= 0; --k)
+            for (int k = 0; k < W; ++k)
             {
-                const float Ak = preA[k] * sufA, Bk = preB[k] * sufB;
-                float mag = 0.6931471805599453f * lg2_approx((Bk + Ak) * rcp_approx(Bk - Ak));
-                mag = fminf(mag, cap); // +inf (saturated product) -> threshold; the clamp of :246-249
-                sufA *= a[k];
-                sufB *= b[k];
+                const float num = fmaf(-e[k], D, S);
+                const float den = fmaf(-e[k], S, D);
+                float mag = lg2_approx(num * rcp_approx(den));
+                mag = fminf(mag, cap);
                 v[k] = __uint_as_float(((xr ^ __float_as_uint(v[k])) & 0x80000000u) | __float_as_uint(mag));
             }
         }
@@ -108,6 +109,7 @@ namespace qlb
 
     struct RuleF32Accurate
     {
+        static constexpr float kUnit = 1.f; // natural-log units
         // libdevice tanhf / atanhf, leave-one-out product by prefix * suffix
         template <int W>
         static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, float cap)
@@ -162,19 +164,19 @@ namespace qlb
         {
             const uint32_t sb = (my_syn >> rbit) & 1u;
             uint32_t xr = sb * 0x80000001u; // bit 31: sign seed, bit 0: parity seed
-            const uint32_t p4 = 4u * p;
+            unsigned char *row = msg_bytes + 4u * p; // + (uniform) row offset per edge position
             float v[W];
 #pragma unroll
             for (int k = 0; k < W; ++k)
             {
-                v[k] = *reinterpret_cast<const float *>(msg_bytes + (base4(k) + p4));
+                v[k] = *reinterpret_cast<const float *>(row + base4(k));
                 xr ^= __float_as_uint(v[k]);
             }
             bad |= xr;
             Rule::template apply<W>(v, xr, cap);
 #pragma unroll
             for (int k = 0; k < W; ++k)
-                *reinterpret_cast<float *>(msg_bytes + (base4(k) + p4)) = v[k];
+                *reinterpret_cast<float *>(row + base4(k)) = v[k];
         }
         return bad;
     }
@@ -190,23 +192,82 @@ namespace qlb
 
     constexpr int kResidentMaxCW = 16;
     constexpr int kResidentThreads = 1024;
+    constexpr size_t kResidentStaticSmem = 2 * kResidentThreads * 4 + 512; // static bookkeeping declared inside the kernel
 
     __host__ __device__ inline size_t resident_smem_bytes(int n, int m, int slots, int bw)
     {
         const size_t wn = align_up((size_t)(n + 31) / 32 * 4, 16), wm = align_up((size_t)(m + 31) / 32 * 4, 16);
-        return align_up((size_t)slots * 4, 16) + align_up((size_t)bw * n * 2, 16) + 3 * wn + wm + 256;
+        return align_up((size_t)slots * 4, 16) + align_up((size_t)bw * n * 2, 16) + 3 * wn + wm;
+    }
+
+    // One bit pass over the thread's bits: total (:256-258), hard decision (:259-266), extrinsic (+ clamp) (:300-316).
+    // kClamp = false when the clamp cannot change what the check rule sees (see decode_resident_f32_kernel).
+    template <bool kReconcile, bool kClamp, int kBW, int kThreads>
+    __device__ __forceinline__ void bit_pass(unsigned char *__restrict__ msg_bytes, const uint16_t *__restrict__ bslot, uint32_t *__restrict__ s_z,
+                                             int n, uint32_t my_bob, float lp, const double *__restrict__ llr_f, float unit, float cap)
+    {
+        const int tid = threadIdx.x;
+        const uint16_t *bs = bslot + tid;
+        uint32_t *zw = s_z + (tid >> 5);
+        const bool lane0 = (tid & 31) == 0;
+#pragma unroll 1
+        for (int i = tid; i < n; i += kThreads)
+        {
+            float prior;
+            if (kReconcile)
+            {
+                prior = __uint_as_float(__float_as_uint(lp) ^ (my_bob << 31));
+                my_bob >>= 1;
+            }
+            else
+                prior = unit * (float)llr_f[i];
+            uint32_t sl[kBW];
+            float c[kBW];
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+                sl[a] = 4u * (uint32_t)bs[a * n];
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+                c[a] = *reinterpret_cast<const float *>(msg_bytes + sl[a]);
+            float total = prior;
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+                total = total + c[a];
+            const bool z = total <= 0.f;
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+            {
+                float v = total - c[a];
+                if (kClamp)
+                    v = fminf(fmaxf(v, -cap), cap);
+                *reinterpret_cast<float *>(msg_bytes + sl[a]) = __uint_as_float((__float_as_uint(v) & ~1u) | (uint32_t)z);
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, z); // n % 32 == 0: whole warps only
+            if (lane0)
+                *zw = word;
+            bs += kThreads;
+            zw += kThreads / 32;
+        }
     }
 
     // kBW: the (uniform) bit weight. Host-checked requirements: slots < 65535, max_check_w <= 16, every bit of weight kBW,
-    // m <= 32 * kThreads and n <= 32 * kThreads (one register bit per visited node).
+    // n % 32 == 0, and m, n <= 32 * kThreads (one register bit per node a thread visits).
     template <typename Rule, bool kReconcile, int kBW, int kThreads>
     __global__ void __launch_bounds__(kThreads, 1) decode_resident_f32_kernel(const DecodeArgs args)
     {
         extern __shared__ __align__(16) unsigned char smem[];
+        // small bookkeeping at fixed (static) shared addresses
+        __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
+        __shared__ uint32_t s_base4[kResidentMaxCW];
+        __shared__ uint32_t s_park_bob[kThreads], s_park_syn[kThreads];
+        __shared__ int s_nseg;
+        __shared__ __align__(8) uint64_t s_bar;
+        __shared__ long long s_frame;
+
         const CodeDev &code = args.code;
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31;
         const int words_n = code.words_n, words_m = code.words_m;
-        const size_t wn = align_up((size_t)words_n * 4, 16), wm = align_up((size_t)words_m * 4, 16);
+        const size_t wn = align_up((size_t)words_n * 4, 16);
         const uint32_t idx_bytes = (uint32_t)align_up((size_t)kBW * n * 2, 16);
 
         float *msg = reinterpret_cast<float *>(smem);
@@ -217,40 +278,50 @@ namespace qlb
         uint32_t *s_alice = reinterpret_cast<uint32_t *>(tail + wn);
         uint32_t *s_z = reinterpret_cast<uint32_t *>(tail + 2 * wn);
         uint32_t *s_synn = reinterpret_cast<uint32_t *>(tail + 3 * wn); // syndrome, natural check order
-        uint32_t *s_cnt = reinterpret_cast<uint32_t *>(tail + 3 * wn + wm); // [17]
-        uint32_t *s_base4 = s_cnt + 18;                                       // [16]
-        uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_base4 + 16);
-        long long *s_frame = reinterpret_cast<long long *>(s_bar + 1);
 
         // stage the bit->slot table: one TMA bulk copy per CTA (the table is 16-byte padded on the device)
         if (tid == 0)
-            mbar_init(s_bar, 1);
-        if (tid <= kResidentMaxCW)
-            s_cnt[tid] = tid < kResidentMaxCW ? code.cnt[tid] : 0;
+        {
+            mbar_init(&s_bar, 1);
+            // weight segments of the sorted checks: [lo, hi) holds the checks of weight exactly w; w = 0 last
+            int ns = 0;
+            for (int w = code.max_check_w; w >= 0; --w)
+            {
+                const uint32_t lo = (w < code.max_check_w) ? code.cnt[w] : 0u, hi = (w > 0) ? code.cnt[w - 1] : (uint32_t)m;
+                if (lo < hi)
+                {
+                    s_seg_w[ns] = (uint32_t)w;
+                    s_seg_lo[ns] = lo;
+                    s_seg_hi[ns] = hi;
+                    ++ns;
+                }
+            }
+            s_nseg = ns;
+        }
         if (tid < kResidentMaxCW)
             s_base4[tid] = code.base4[tid];
         __syncthreads();
         if (tid == 0)
         {
-            mbar_expect_tx(s_bar, idx_bytes);
-            tma_bulk_g2s(bslot, code.bit_slots16, idx_bytes, s_bar);
+            mbar_expect_tx(&s_bar, idx_bytes);
+            tma_bulk_g2s(bslot, code.bit_slots16, idx_bytes, &s_bar);
         }
-        mbar_wait(s_bar, 0);
+        mbar_wait(&s_bar, 0);
 
-        const int wmax = code.max_check_w;
-        const float cap = args.cap_f32;
-        const uint16_t *bs[kBW];
-#pragma unroll
-        for (int a = 0; a < kBW; ++a)
-            bs[a] = bslot + a * n;
+        const float unit = Rule::kUnit;
+        const float cap = args.cap_f32 * unit;
+        // Below |m| = 2^-25-resolution the fast rule maps every message to exactly (1-e, 1+e) = (1, 1): clamping bit-to-check
+        // messages at a threshold >= 25 base-2 units cannot change any later value, so that clamp is skipped.
+        const bool clamp_b2c = !(Rule::kUnit != 1.f && cap >= 25.f);
+        const int nseg = s_nseg;
 
         for (;;)
         {
             __syncthreads();
             if (tid == 0)
-                *s_frame = (long long)atomicAdd(args.queue, 1ULL);
+                s_frame = (long long)atomicAdd(args.queue, 1ULL);
             __syncthreads();
-            const long long f = *s_frame;
+            const long long f = s_frame;
             if (f >= args.n_frames)
                 break;
 
@@ -259,7 +330,7 @@ namespace qlb
             const double *llr_f = nullptr;
             if (kReconcile)
             {
-                lp = (float)args.log_prior[f];
+                lp = unit * (float)args.log_prior[f];
                 for (int w = tid; w < words_n; w += kThreads)
                 {
                     s_bob[w] = args.bob[f * words_n + w];
@@ -277,10 +348,10 @@ namespace qlb
             __syncthreads();
 
             // messages <- priors (src/qkd_ldpc_algorithm.cpp:182-190); in reconcile mode Alice's bit rides in bit 0 so
-            // that the parity of the first walk over the checks is her syndrome (:413-414). my_bob: Bob's bit of the
-            // r-th bit this thread visits.
-            uint32_t my_bob = 0;
+            // that the parity of the first walk over the checks is her syndrome (:413-414). Bob's bit of the r-th bit this
+            // thread visits is parked as bit r of s_park_bob[tid].
             {
+                uint32_t my_bob = 0;
                 int r = 0;
                 for (int i = tid; i < n; i += kThreads, ++r)
                 {
@@ -294,23 +365,24 @@ namespace qlb
                         prior = bb ? -lp : lp;
                     }
                     else
-                        prior = (float)llr_f[i];
+                        prior = unit * (float)llr_f[i];
                     const float pv = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
 #pragma unroll
                     for (int a = 0; a < kBW; ++a)
-                        msg[bs[a][i]] = pv;
+                        msg[bslot[a * n + i]] = pv;
                 }
+                s_park_bob[tid] = my_bob;
             }
             __syncthreads();
 
-            // my_syn: target syndrome bit of the r-th check this thread visits (same walk as the check pass)
-            uint32_t my_syn = 0;
+            // target syndrome bit of the r-th check this thread visits (same walk as the check pass) -> bit r
             {
+                uint32_t my_syn = 0;
                 int r = 0;
-                for (int w = wmax; w >= 0; --w)
+                for (int sg = 0; sg < nseg; ++sg)
                 {
-                    const uint32_t lo = (w < wmax) ? s_cnt[w] : 0u, hi = (w > 0) ? s_cnt[w - 1] : (uint32_t)m;
-                    for (uint32_t p = lo + tid; p < hi; p += kThreads, ++r)
+                    const int w = (int)s_seg_w[sg];
+                    for (uint32_t p = s_seg_lo[sg] + tid; p < s_seg_hi[sg]; p += kThreads, ++r)
                     {
                         const uint32_t j = code.check_order[p];
                         uint32_t bit = 0;
@@ -327,6 +399,7 @@ namespace qlb
                         my_syn |= bit << r;
                     }
                 }
+                s_park_syn[tid] = my_syn;
             }
             // (no barrier needed: every thread only re-reads the slots of its own checks next)
 
@@ -338,27 +411,28 @@ namespace qlb
             for (;;)
             {
                 uint32_t bad = 0;
-                int rbit = 0;
-#pragma unroll 1
-                for (int w = wmax; w >= 1; --w)
                 {
-                    const uint32_t lo = (w < wmax) ? s_cnt[w] : 0u, hi = s_cnt[w - 1];
-                    if (lo >= hi)
-                        continue;
-                    switch (w)
+                    const uint32_t my_syn = s_park_syn[tid];
+                    int rbit = 0;
+#pragma unroll 1
+                    for (int sg = 0; sg < nseg; ++sg)
                     {
+                        const uint32_t lo = s_seg_lo[sg], hi = s_seg_hi[sg];
+                        switch (s_seg_w[sg])
+                        {
 #define QLB_SEG(W_) case W_: bad |= check_segment<Rule, W_, kThreads>(msg_bytes, BaseFromParams{args}, lo, hi, my_syn, rbit, cap); break;
 #define QLB_SEGW(W_) case W_: { const uint32_t rv = check_segment_wide<Rule, W_, kThreads>(msg_bytes, s_base4, lo, hi, my_syn, rbit, cap); bad |= rv & 1u; rbit = (int)(rv >> 1); } break;
-                        QLB_SEG(1) QLB_SEG(2) QLB_SEG(3) QLB_SEG(4) QLB_SEG(5) QLB_SEG(6) QLB_SEG(7) QLB_SEG(8)
-                        QLB_SEGW(9) QLB_SEGW(10) QLB_SEGW(11) QLB_SEGW(12) QLB_SEGW(13) QLB_SEGW(14) QLB_SEGW(15) QLB_SEGW(16)
+                            QLB_SEG(1) QLB_SEG(2) QLB_SEG(3) QLB_SEG(4) QLB_SEG(5) QLB_SEG(6) QLB_SEG(7) QLB_SEG(8)
+                            QLB_SEGW(9) QLB_SEGW(10) QLB_SEGW(11) QLB_SEGW(12) QLB_SEGW(13) QLB_SEGW(14) QLB_SEGW(15) QLB_SEGW(16)
 #undef QLB_SEG
 #undef QLB_SEGW
-                    default: break;
+                        default: // checks without edges can only be satisfied by a zero syndrome bit
+                            for (uint32_t p = lo + tid; p < hi; p += kThreads, ++rbit)
+                                bad |= (my_syn >> rbit) & 1u;
+                            break;
+                        }
                     }
                 }
-                // checks without edges can only be satisfied by a zero syndrome bit
-                for (uint32_t p = s_cnt[0] + tid; p < (uint32_t)m; p += kThreads, ++rbit)
-                    bad |= (my_syn >> rbit) & 1u;
                 const int any_bad = __syncthreads_or((int)(bad & 1u));
                 if (it > 0 && !any_bad)
                 {
@@ -367,44 +441,10 @@ namespace qlb
                 }
                 if (it == args.max_it)
                     break; // :337-344
-                // bit pass: total (:256-258), decision (:259-266), extrinsic + clamp (:300-316)
-                {
-                    int r = 0;
-#pragma unroll 1
-                    for (int i = tid; i < n; i += kThreads, ++r)
-                    {
-                        float prior;
-                        if (kReconcile)
-                            prior = __uint_as_float(__float_as_uint(lp) ^ (((my_bob >> r) & 1u) << 31));
-                        else
-                            prior = (float)llr_f[i];
-                        uint32_t sl[kBW];
-                        float c[kBW];
-#pragma unroll
-                        for (int a = 0; a < kBW; ++a)
-                            sl[a] = 4u * (uint32_t)bs[a][i];
-#pragma unroll
-                        for (int a = 0; a < kBW; ++a)
-                            c[a] = *reinterpret_cast<const float *>(msg_bytes + sl[a]);
-                        float total = prior;
-#pragma unroll
-                        for (int a = 0; a < kBW; ++a)
-                            total = total + c[a];
-                        const bool z = total <= 0.f;
-#pragma unroll
-                        for (int a = 0; a < kBW; ++a)
-                        {
-                            float v = total - c[a];
-                            v = fminf(fmaxf(v, -cap), cap);
-                            *reinterpret_cast<float *>(msg_bytes + sl[a]) = __uint_as_float((__float_as_uint(v) & ~1u) | (uint32_t)z);
-                        }
-                        // lanes of one warp leave this loop together except in the last, partial word of the key
-                        const uint32_t lanes = (i - lane + 32 <= n) ? 0xffffffffu : ((1u << (n & 31)) - 1u);
-                        const uint32_t word = __ballot_sync(lanes, z);
-                        if (lane == 0)
-                            s_z[i >> 5] = word;
-                    }
-                }
+                if (clamp_b2c)
+                    bit_pass<kReconcile, true, kBW, kThreads>(msg_bytes, bslot, s_z, n, s_park_bob[tid], lp, llr_f, unit, cap);
+                else
+                    bit_pass<kReconcile, false, kBW, kThreads>(msg_bytes, bslot, s_z, n, s_park_bob[tid], lp, llr_f, unit, cap);
                 ++it;
                 __syncthreads();
             }
