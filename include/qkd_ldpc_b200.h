@@ -171,6 +171,17 @@ int qlb_reconcile_device(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_pa
                          uint32_t *d_iterations_out, uint8_t *d_result_out, uint32_t *d_decoded_packed_out,
                          uint32_t *d_syndrome_packed_out);
 
+/* ---- sweep statistics ---------------------------------------------------------------------------
+ * The one collective of a sweep: element-wise SUM over the GPUs of one process of per-GPU integer statistics
+ * (histogram of iterations_num over successful frames + counters; the quantities the reference accumulates serially at
+ * src/simulation.cpp:252-312). vectors[g] is a HOST array of `count` uint64 owned by the caller for ctxs[g]; on return
+ * every vectors[g] holds the sum. One ncclAllReduce per GPU inside a group call over NVLink (libnccl.so.2 is loaded on
+ * first use; QLB_ERR_NCCL when it is missing or fails). With n_ctx == 1 the call is a device round trip through NCCL.
+ * (Across processes -- one rank per GPU under torchrun -- the same reduction is done with torch.distributed/NCCL by
+ * qkd_ldpc_b200/sweep.py.)
+ */
+int qlb_stats_allreduce(qlb_ctx *const *ctxs, int n_ctx, uint64_t *const *vectors, size_t count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ EXPORTS = [
     "qlb_ctx_create", "qlb_ctx_destroy", "qlb_ctx_device", "qlb_ctx_sm_count", "qlb_ctx_stream", "qlb_ctx_synchronize",
     "qlb_ctx_counters", "qlb_ctx_timer_start", "qlb_ctx_timer_stop",
     "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch",
-    "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device",
+    "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device", "qlb_stats_allreduce",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.qlb_reconcile_batch.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_reconcile_batch_packed.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_reconcile_device.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.qlb_stats_allreduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_size_t]
     if path is None:
         _lib = lib
     return lib
@@ -271,6 +272,16 @@ class Context:
                          d_decoded=None, d_syndrome=None):
         _check(self.lib, self.lib.qlb_reconcile_device(self.handle, code.handle, C.byref(params), int(n_frames), d_alice, d_bob,
                                                        d_log_prior, d_iterations, d_result, d_decoded, d_syndrome))
+
+    def stats_allreduce(self, vectors, others=()):
+        """In-process NCCL sum of uint64 statistics over this context and `others` (one vector per context)."""
+        ctxs = [self, *others]
+        vecs = [np.ascontiguousarray(v, np.uint64) for v in vectors]
+        assert len(vecs) == len(ctxs)
+        cs = (C.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+        ps = (C.c_void_p * len(ctxs))(*[v.ctypes.data for v in vecs])
+        _check(self.lib, self.lib.qlb_stats_allreduce(cs, len(ctxs), ps, vecs[0].size))
+        return vecs
 
     def close(self):
         if getattr(self, "handle", None):

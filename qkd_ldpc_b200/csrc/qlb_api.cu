@@ -7,6 +7,7 @@
 #include "qlb_layout.hpp"
 
 #include <atomic>
+#include <dlfcn.h>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -736,6 +737,91 @@ extern "C"
         QLB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (bits_out)
             unpack_frames(ctx->host_pack_out.data(), n_frames, L.n, L.words_n, bits_out);
+        return QLB_OK;
+    }
+
+    // ---- statistics all-reduce over the GPUs of this process (NCCL, loaded lazily) ---------------------------------------
+    int qlb_stats_allreduce(qlb_ctx *const *ctxs, int n_ctx, uint64_t *const *vectors, size_t count)
+    {
+        if (!ctxs || !vectors || n_ctx < 1 || count == 0)
+            return fail(QLB_ERR_INVALID, "qlb_stats_allreduce: bad arguments");
+        typedef void *comm_t;
+        typedef int (*init_all_t)(comm_t *, int, const int *);
+        typedef int (*allreduce_t)(const void *, void *, size_t, int, int, comm_t, cudaStream_t);
+        typedef int (*group_t)(void);
+        typedef const char *(*errstr_t)(int);
+        struct nccl_api
+        {
+            void *lib = nullptr;
+            init_all_t init_all = nullptr;
+            allreduce_t allreduce = nullptr;
+            group_t group_start = nullptr, group_end = nullptr;
+            errstr_t errstr = nullptr;
+            std::map<std::vector<int>, std::vector<comm_t>> comms;
+            std::mutex mu;
+        };
+        static nccl_api api;
+        std::lock_guard<std::mutex> lk(api.mu);
+        if (!api.lib)
+        {
+            api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!api.lib)
+                return fail(QLB_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+            api.init_all = (init_all_t)dlsym(api.lib, "ncclCommInitAll");
+            api.allreduce = (allreduce_t)dlsym(api.lib, "ncclAllReduce");
+            api.group_start = (group_t)dlsym(api.lib, "ncclGroupStart");
+            api.group_end = (group_t)dlsym(api.lib, "ncclGroupEnd");
+            api.errstr = (errstr_t)dlsym(api.lib, "ncclGetErrorString");
+            if (!api.init_all || !api.allreduce || !api.group_start || !api.group_end)
+                return fail(QLB_ERR_NCCL, "libnccl.so.2 lacks the expected entry points");
+        }
+        auto nccl_fail = [&](int rc, const char *what)
+        { return fail(QLB_ERR_NCCL, std::string(what) + ": " + (api.errstr ? api.errstr(rc) : "NCCL error")); };
+        std::vector<int> devs;
+        for (int g = 0; g < n_ctx; ++g)
+        {
+            if (!ctxs[g] || !vectors[g])
+                return fail(QLB_ERR_INVALID, "qlb_stats_allreduce: null context or vector");
+            devs.push_back(ctxs[g]->device);
+        }
+        auto it = api.comms.find(devs);
+        if (it == api.comms.end())
+        {
+            std::vector<comm_t> comms(n_ctx, nullptr);
+            const int rc = api.init_all(comms.data(), n_ctx, devs.data());
+            if (rc != 0)
+                return nccl_fail(rc, "ncclCommInitAll");
+            it = api.comms.emplace(devs, comms).first;
+        }
+        const size_t bytes = count * sizeof(uint64_t);
+        for (int g = 0; g < n_ctx; ++g)
+        {
+            QLB_CUDA(cudaSetDevice(ctxs[g]->device));
+            QLB_CUDA(ctxs[g]->in_q.reserve(bytes));
+            QLB_CUDA(cudaMemcpyAsync(ctxs[g]->in_q.p, vectors[g], bytes, cudaMemcpyHostToDevice, ctxs[g]->stream));
+        }
+        int rc = api.group_start();
+        if (rc != 0)
+            return nccl_fail(rc, "ncclGroupStart");
+        for (int g = 0; g < n_ctx; ++g)
+        {
+            QLB_CUDA(cudaSetDevice(ctxs[g]->device));
+            rc = api.allreduce(ctxs[g]->in_q.p, ctxs[g]->in_q.p, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, it->second[g], ctxs[g]->stream);
+            if (rc != 0)
+            {
+                api.group_end();
+                return nccl_fail(rc, "ncclAllReduce");
+            }
+        }
+        rc = api.group_end();
+        if (rc != 0)
+            return nccl_fail(rc, "ncclGroupEnd");
+        for (int g = 0; g < n_ctx; ++g)
+        {
+            QLB_CUDA(cudaSetDevice(ctxs[g]->device));
+            QLB_CUDA(cudaMemcpyAsync(vectors[g], ctxs[g]->in_q.p, bytes, cudaMemcpyDeviceToHost, ctxs[g]->stream));
+            QLB_CUDA(cudaStreamSynchronize(ctxs[g]->stream));
+        }
         return QLB_OK;
     }
 }

@@ -293,7 +293,7 @@ namespace qlb
     // The decoder. kShapeW: 0 = any node weights (two-pass check rule, re-gathering bit pass);
     //                       8 / 16 = register tiles for checks of weight <= 8 / 16 and bits of weight <= 4.
     template <typename Math, int kTier, bool kReconcile, int kShapeW, int kThreads>
-    __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const DecodeArgs args)
+    __global__ void __launch_bounds__(kThreads, kThreads <= 512 ? 2 : 1) decode_kernel(const DecodeArgs args)
     {
         typedef typename Math::real Real;
         typedef typename std::conditional<kTier == kTierGlobal, uint32_t, uint16_t>::type IdxT;

@@ -1,0 +1,165 @@
+"""The host-side C++ mirror of the reference API (qkd_ldpc_b200/host): loaders, key generator and config handling on
+the CPU; the config.json-driven sweep against the reference's own CSV output on the GPU."""
+import json
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, NS, ROOT
+from qkd_ldpc_b200 import build, codes
+
+SIM = build.SIM_PATH
+
+
+@pytest.fixture(scope="module")
+def sim():
+    build.build_all()
+    assert SIM.exists()
+    return SIM
+
+
+def run(sim, *args, cwd=None, check=True):
+    p = subprocess.run([str(sim), *map(str, args)], capture_output=True, text=True, cwd=cwd)
+    if check:
+        assert p.returncode == 0, p.stderr
+    return p
+
+
+def parse_dump(text):
+    lines = text.strip().splitlines()
+    n, m, mbw, mcw, reg = map(int, lines[0].split())
+    bit_lists = [list(map(int, ln.split()))[1:] for ln in lines[1:1 + n]]
+    check_lists = [list(map(int, ln.split()))[1:] for ln in lines[1 + n:1 + n + m]]
+    return n, m, mbw, mcw, bool(reg), bit_lists, check_lists
+
+
+@pytest.mark.parametrize("name", ["dense_n6_m4", "dense_n7_m3", "dense_n10_m5", NS])
+def test_cpp_loaders_match_reference_matrices(sim, matrices, name):
+    """read_dense_matrix / read_sparse_alist_matrix produce the H_matrix the reference's loaders produced (data/codes/*.npz
+    hold the reference's own output)."""
+    mat = matrices[name]
+    path = codes.materialize()[name]
+    n, m, mbw, mcw, reg, bit_lists, check_lists = parse_dump(run(sim, "--dump-matrix", "dense" if name.startswith("dense") else "alist", path).stdout)
+    assert (n, m, reg) == (mat.n, mat.m, mat.is_regular)
+    assert (mbw, mcw) == (mat.max_bit_w, mat.max_check_w)
+    assert sum(bit_lists, []) == mat.row_idx.tolist() and sum(check_lists, []) == mat.col_idx.tolist()
+    assert [len(b) for b in bit_lists] == np.diff(mat.col_ptr).tolist()
+
+
+def test_cpp_loader_errors(sim, tmp_path):
+    bad = tmp_path / "bad.txt"
+    bad.write_text("1 0 2\n0 1 1\n")
+    p = run(sim, "--dump-matrix", "dense", bad, check=False)
+    assert p.returncode != 0 and "can only take values" in p.stderr
+    bad.write_text("1 1 1\n0 0 0\n")
+    p = run(sim, "--dump-matrix", "dense", bad, check=False)
+    assert p.returncode != 0 and "Row '2' weight cannot be equal to or less than zero" in p.stderr
+    bad.write_text("3 2\n2 2\n1 1 2\n2 2\n1 0\n2 0\n1 0\n1 3\n2 3\n")      # column 3 lists one entry, declares two
+    p = run(sim, "--dump-matrix", "alist", bad, check=False)
+    assert p.returncode != 0 and "does not match the weight" in p.stderr
+    p = run(sim, "--dump-matrix", "alist", tmp_path / "missing.txt", check=False)
+    assert p.returncode != 0 and "Failed to open file" in p.stderr
+
+
+def test_cpp_generator_matches_oracle(sim, oracle):
+    """Same seeds -> same Alice/Bob keys as the (reference-pinned) oracle generator, including the shuffle."""
+    assert run(sim, "--seeds", 777, 3).stdout.split() == [str(v) for v in oracle.trial_seeds(777, 3)]
+    for seed, n, q in [(int(oracle.trial_seeds(777, 1)[0]), 10240, 0.03), (12345, 7, 0.25), (99, 33, 0.5), (5, 64, 0.01)]:
+        out = run(sim, "--gen", seed, n, q).stdout.split()
+        a, b, exact = oracle.generate(seed, n, q)
+        assert float(out[0]) == exact
+        assert out[1] == "".join(map(str, a)) and out[2] == "".join(map(str, b))
+
+
+def base_cfg(**kw):
+    cfg = {"threads_number": 8, "trials_number": 64, "use_config_simulation_seed": True, "simulation_seed": 777,
+           "interactive_mode": False, "sum_product_max_iterations": 100, "use_dense_matrices": False, "trace_qkd_ldpc": False,
+           "trace_sum_product": False, "trace_sum_product_llr": False, "enable_sum_product_msg_llr_threshold": True,
+           "sum_product_msg_llr_threshold": 100.0,
+           "code_rate_QBER_parameters": [{"code_rate": 0.5, "QBER_begin": 0.03, "QBER_end": 0.12, "QBER_step": 0.01}]}
+    cfg.update(kw)
+    return cfg
+
+
+def make_dir(tmp_path, cfg, name, dense):
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    sub = tmp_path / ("dense_matrices" if dense else "alist_sparse_matrices")
+    sub.mkdir()
+    shutil.copy(codes.materialize()[name], sub)
+    return tmp_path
+
+
+def test_cpp_config_validation(sim, tmp_path):
+    d = make_dir(tmp_path, base_cfg(trials_number=0), NS, False)
+    p = run(sim, d, check=False)
+    assert p.returncode != 0 and "Number of trials must be >= 1!" in p.stderr
+    (d / "config.json").write_text(json.dumps(base_cfg(code_rate_QBER_parameters=[{"code_rate": 0.5, "QBER_begin": 0.2, "QBER_end": 0.1, "QBER_step": 0.01}])))
+    p = run(sim, d, check=False)
+    assert p.returncode != 0 and "Invalid QBER begin or end parameters" in p.stderr
+    (d / "config.json").write_text(json.dumps(base_cfg(code_rate_QBER_parameters=[{"code_rate": 0.3, "QBER_begin": 0.03, "QBER_end": 0.12, "QBER_step": 0.01}])))
+    p = run(sim, d, check=False)
+    assert p.returncode != 0 and "QBER range based on code rate" in p.stderr
+    (d / "config.json").unlink()
+    p = run(sim, d, check=False)
+    assert p.returncode != 0 and "Configuration file not found" in p.stderr
+
+
+def test_cpp_no_gpu_fails_loudly(sim, tmp_path, lib):
+    if lib.qlb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    d = make_dir(tmp_path, base_cfg(trials_number=4), NS, False)
+    p = run(sim, d, check=False)
+    assert p.returncode != 0 and "no CPU decoder" in p.stderr
+
+
+@pytest.mark.gpu
+def test_sweep_csv_equals_reference_north_star(sim, tmp_path):
+    """config.json -> CSV on the N=10240 code, 64 trials x 9 QBER points: byte-identical to the CSV written by the
+    reference's own main() (tests/golden/sweep_n10240_t64_seed777.csv), fp64 messages."""
+    d = make_dir(tmp_path, base_cfg(), NS, False)
+    run(sim, d)
+    out = sorted((d / "results").glob("*.csv"))
+    assert len(out) == 1 and out[0].name == "ldpc(trial_num=64,max_sum_prod_iters=100,seed=777).csv"
+    assert out[0].read_text() == (GOLD / "sweep_n10240_t64_seed777.csv").read_text()
+
+
+@pytest.mark.gpu
+def test_sweep_csv_equals_reference_dense_n7(sim, tmp_path):
+    """BASELINE.json configs[0]: dense (N=7,K=4,M=3) through config.json, 1000 trials, two QBER points."""
+    cfg = base_cfg(trials_number=1000, use_dense_matrices=True, device_batch_frames=256,
+                   code_rate_QBER_parameters=[{"code_rate": 0.58, "QBER_begin": 0.15, "QBER_end": 0.35, "QBER_step": 0.1}])
+    d = make_dir(tmp_path, cfg, "dense_n7_m3", True)
+    run(sim, d)
+    out = sorted((d / "results").glob("*.csv"))
+    assert out[0].read_text() == (GOLD / "sweep_dense_n7_t1000_seed777.csv").read_text()
+    # a second run must not overwrite: the reference de-duplicates the file name
+    run(sim, d)
+    assert len(sorted((d / "results").glob("*.csv"))) == 2
+
+
+@pytest.mark.gpu
+def test_sweep_fp32_and_forced_allreduce(sim, tmp_path, monkeypatch):
+    """fp32 fast path through config.json (same FER / ratios on this grid; iteration means within a few percent), with the
+    NCCL statistics all-reduce forced on the single GPU."""
+    import os
+    d = make_dir(tmp_path, base_cfg(device_precision=32, device_fp32_fast_math=True), NS, False)
+    env = dict(os.environ, QKD_B200_FORCE_ALLREDUCE="1")
+    p = subprocess.run([str(sim), str(d)], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    got = [ln.split(";") for ln in sorted((d / "results").glob("*.csv"))[0].read_text().splitlines()[1:]]
+    want = [ln.split(";") for ln in (GOLD / "sweep_n10240_t64_seed777.csv").read_text().splitlines()[1:]]
+    for g, w in zip(got, want):
+        assert g[:7] == w[:7] and g[11:] == w[11:], (g, w)          # identity columns, success ratios, FER
+        assert abs(float(g[7]) - float(w[7])) <= 0.05 * float(w[7]) + 1e-9
+
+
+@pytest.mark.gpu
+def test_key_too_small_error(sim, tmp_path):
+    cfg = base_cfg(use_dense_matrices=True, trials_number=4,
+                   code_rate_QBER_parameters=[{"code_rate": 0.58, "QBER_begin": 0.05, "QBER_end": 0.1, "QBER_step": 0.05}])
+    d = make_dir(tmp_path, cfg, "dense_n7_m3", True)
+    p = run(sim, d, check=False)
+    assert p.returncode != 0 and "Key size '7' is too small for QBER." in p.stderr
