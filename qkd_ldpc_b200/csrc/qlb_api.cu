@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -202,6 +203,9 @@ namespace
             args.scratch = static_cast<unsigned char *>(ctx->scratch.p);
             args.scratch_stride = cv.total_scratch;
         }
+        if (std::getenv("QLB_DEBUG"))
+            std::fprintf(stderr, "[qlb] decode_kernel tier=%d reconcile=%d shapeW=%d threads=%d: %d CTA/SM, grid=%lld, smem=%zu B, scratch=%zu B/CTA\n",
+                         kTier, (int)kReconcile, kShapeW, kThreads, per_sm, grid, cv.total_smem, cv.total_scratch);
         QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;
