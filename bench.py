@@ -128,7 +128,7 @@ def cpu_reference_sweep(trials_per_point: int, threads: int, seed: int = 777):
     return kind, time.perf_counter() - t0, outs
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, guard):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -150,14 +150,14 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "decoded_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(tpp, "f64"),
+        "config": workload_config(args.frames_per_point, args.precision),  # the measured arm's config; the sample is below
         "sifted_mbit_s": value * 10240 / 1e6,
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "per_qber": [{"qber": q, "fer": f} for q, f in zip(grid, fer)],
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    guard.emit(line)
     return 0
 
 
@@ -173,7 +173,22 @@ def workload_config(frames_per_point, precision):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class StdoutGuard:
+    """The contract is ONE JSON line on stdout: anything libraries print to fd 1 meanwhile (e.g. NCCL's version banner) is
+    sent to stderr, and the line is written to the real stdout at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: dict):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -189,7 +204,7 @@ def main():
         args.warmup = max(args.warmup, 1)
 
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, guard)
 
     import torch
     import torch.distributed as dist
@@ -405,7 +420,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "per_qber": per_qber, "fer_parity_vs_cpu_sample": fer_parity, "variants": variants,
         }
-        print(json.dumps(line), flush=True)
+        guard.emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -27,7 +27,7 @@ HOST_CXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else (shutil.which("g
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+    "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", *os.environ.get("QLB_NVCC_EXTRA", "").split(),
 ]
 
 

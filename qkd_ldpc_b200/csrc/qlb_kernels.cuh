@@ -98,6 +98,18 @@ namespace qlb
     struct MathF64
     {
         typedef double real;
+#ifdef QLB_F64_ALGEBRAIC
+        // experiment: branch-free algebraic forms (same functions, different rounding at the ulp level)
+        static __device__ __forceinline__ double tanh_half(double m)
+        {
+            const double e = exp(-fmin(fabs(m), 64.));
+            return copysign((1. - e) / (1. + e), m);
+        }
+        static __device__ __forceinline__ double two_atanh(double p) { return log((1. + p) / (1. - p)); }
+#else
+        static __device__ __forceinline__ double tanh_half(double m) { return tanh(m / 2.); }
+        static __device__ __forceinline__ double two_atanh(double p) { return 2. * atanh(p); }
+#endif
         template <int W>
         static __device__ __forceinline__ void check(double (&v)[W], int w, bool s, bool en, double thr)
         {
@@ -106,13 +118,13 @@ namespace qlb
             for (int k = 0; k < W; ++k)
                 if (k < w)
                 {
-                    v[k] = tanh(v[k] / 2.);
+                    v[k] = tanh_half(v[k]);
                     row *= v[k];
                 }
 #pragma unroll
             for (int k = 0; k < W; ++k)
                 if (k < w)
-                    v[k] = clamp_msg(2. * atanh(row / v[k]), thr, en);
+                    v[k] = clamp_msg(two_atanh(row / v[k]), thr, en);
         }
     };
 
@@ -200,8 +212,8 @@ namespace qlb
     struct TwoPass<MathF64>
     {
         static constexpr bool kZeroAware = false; // the reference divides, 0/0 included
-        static __device__ __forceinline__ double t(double m) { return tanh(m / 2.); }
-        static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(2. * atanh(p), thr, en); }
+        static __device__ __forceinline__ double t(double m) { return MathF64::tanh_half(m); }
+        static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(MathF64::two_atanh(p), thr, en); }
     };
     template <>
     struct TwoPass<MathF32>
