@@ -164,3 +164,33 @@ def materialize() -> dict:
             (write_dense if bool(z["dense"]) else write_alist)(mat, dst)
         out[p.stem] = dst
     return out
+
+
+def peg_code(n: int, m: int, dv: int = 3, seed: int = 666, bfs_limit: int = 4096) -> Matrix:
+    """A seeded PEG code of column weight `dv` (host/peg.cpp), cached as alist under data/_generated/peg/ -- the
+    construction the shipped N=10240 code is consistent with; used for BASELINE.json configs[3] and configs[4]."""
+    import subprocess
+    from . import build
+    rate = 1.0 - m / n
+    path = GENERATED / "peg" / f"(N={n},M={m},R={rate:.2f},CW={dv},SEED={seed}).txt"
+    if not path.exists():
+        build.build_host()
+        subprocess.run([str(build.SIM_PATH), "--peg", str(n), str(m), str(dv), str(seed), str(path), str(bfs_limit)], check=True)
+    return read_alist_fast(path)
+
+
+def read_alist_fast(path) -> Matrix:
+    """read_alist without the per-line validation loops (generated files, up to millions of lines)."""
+    with open(path) as f:
+        n, m = map(int, f.readline().split())
+        max_bw, max_cw = map(int, f.readline().split())
+        bw = np.array(f.readline().split(), np.int64)
+        cw = np.array(f.readline().split(), np.int64)
+        rows = [np.array(f.readline().split(), np.int64) for _ in range(n)]
+        cols = [np.array(f.readline().split(), np.int64) for _ in range(m)]
+    row_idx = np.concatenate([r[:w] for r, w in zip(rows, bw)]) - 1
+    col_idx = np.concatenate([c[:w] for c, w in zip(cols, cw)]) - 1
+    col_ptr = np.zeros(n + 1, np.int32); col_ptr[1:] = np.cumsum(bw)
+    row_ptr = np.zeros(m + 1, np.int32); row_ptr[1:] = np.cumsum(cw)
+    regular = bool((bw == bw[0]).all() and (cw == cw[0]).all())
+    return Matrix(n, m, row_ptr, col_idx.astype(np.int32), col_ptr, row_idx.astype(np.int32), regular, max_bw, max_cw, Path(path).name)

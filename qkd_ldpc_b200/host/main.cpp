@@ -33,6 +33,7 @@ std::vector<fs::path> get_file_paths_in_directory(const fs::path &directory_path
 //   --dump-matrix <alist|dense> <file>   prints the loaded H_matrix
 //   --gen <seed> <n> <qber>              prints the exact QBER and Alice's / Bob's keys of one trial
 //   --seeds <seed> <count>               prints raw xoshiro256++ outputs
+//   --peg <n> <m> <dv> <seed> <out> [lim] writes a seeded PEG code as alist (configs[3], configs[4] of BASELINE.json)
 static int inspect(int argc, char **argv)
 {
     const std::string mode = argv[1];
@@ -87,7 +88,13 @@ static int inspect(int argc, char **argv)
             std::cout << prng() << "\n";
         return EXIT_SUCCESS;
     }
-    std::cerr << "usage: qkd_ldpc_b200_sim [dir] | --dump-matrix <alist|dense> <file> | --gen <seed> <n> <qber> | --seeds <seed> <count>\n";
+    if (mode == "--peg" && (argc == 7 || argc == 8))
+    {
+        qkd_b200::generate_peg_alist(std::strtoull(argv[2], nullptr, 10), std::strtoull(argv[3], nullptr, 10), std::strtoull(argv[4], nullptr, 10),
+                                     std::strtoull(argv[5], nullptr, 10), argc == 8 ? std::strtoull(argv[7], nullptr, 10) : 4096, argv[6]);
+        return EXIT_SUCCESS;
+    }
+    std::cerr << "usage: qkd_ldpc_b200_sim [dir] | --peg <n> <m> <col_weight> <seed> <out.alist> [bfs_limit] | --dump-matrix <alist|dense> <file> | --gen <seed> <n> <qber> | --seeds <seed> <count>\n";
     return EXIT_FAILURE;
 }
 

@@ -149,5 +149,7 @@ namespace qkd_b200
         int gpus{};
     };
     const sweep_report &last_sweep_report();
+    // Seeded PEG construction of a column-weight-`dv` code, written as an alist file (host/peg.cpp).
+    void generate_peg_alist(size_t n, size_t m, size_t dv, uint64_t seed, size_t bfs_limit, const fs::path &out_path);
     void release_device_state(); // frees cached device codes / contexts (also done at process exit)
 }
