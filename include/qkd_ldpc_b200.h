@@ -171,6 +171,24 @@ int qlb_reconcile_device(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_pa
                          uint32_t *d_iterations_out, uint8_t *d_result_out, uint32_t *d_decoded_packed_out,
                          uint32_t *d_syndrome_packed_out);
 
+/* ---- key / error generation on the device ---------------------------------------------------------
+ * Replaces, bit for bit, the inputs run_trial builds per trial (src/simulation.cpp:163-169): Alice's key from
+ * generate_random_bit_array and Bob's from introduce_errors (src/array_and_matrix_operations.cpp:424-460), drawn from
+ * XoshiroCpp::Xoshiro256PlusPlus(seeds[f] + seed_offset) with libstdc++ 13.3's uniform_int_distribution / std::shuffle
+ * semantics. `qber` is the requested error probability; exactly floor(n_bits * qber) positions are flipped and
+ * *exact_qber_out (optional) receives that count / n_bits. Fails with QLB_ERR_KEY_TOO_SMALL when it is zero
+ * (the reference throws "Key size ... is too small for QBER.", src/simulation.cpp:170-175).
+ * Keys come back packed; the _device form writes device buffers on the context's stream and does not synchronize.
+ */
+int qlb_generate_batch_packed(qlb_ctx *ctx, int32_t n_bits, int64_t n_frames, const uint64_t *seeds, uint64_t seed_offset, double qber,
+                              uint32_t *alice_packed_out, uint32_t *bob_packed_out, double *exact_qber_out);
+int qlb_generate_device(qlb_ctx *ctx, int32_t n_bits, int64_t n_frames, const uint64_t *d_seeds, uint64_t seed_offset, double qber,
+                        uint32_t *d_alice_packed_out, uint32_t *d_bob_packed_out, double *exact_qber_out);
+/* run_trial for a batch (src/simulation.cpp:161-189): keys generated on the device from the trial seeds, then reconciled;
+ * only 8 bytes per frame go up and 5 come back. Host buffers. */
+int qlb_run_trials(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames, const uint64_t *seeds,
+                   uint64_t seed_offset, double qber, uint32_t *iterations_out, uint8_t *result_out, double *exact_qber_out);
+
 /* ---- sweep statistics ---------------------------------------------------------------------------
  * The one collective of a sweep: element-wise SUM over the GPUs of one process of per-GPU integer statistics
  * (histogram of iterations_num over successful frames + counters; the quantities the reference accumulates serially at

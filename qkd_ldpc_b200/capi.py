@@ -27,6 +27,7 @@ EXPORTS = [
     "qlb_ctx_counters", "qlb_ctx_timer_start", "qlb_ctx_timer_stop",
     "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch",
     "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device", "qlb_stats_allreduce",
+    "qlb_generate_batch_packed", "qlb_generate_device", "qlb_run_trials",
 ]
 
 
@@ -91,6 +92,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.qlb_reconcile_batch_packed.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_reconcile_device.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_stats_allreduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_size_t]
+    dp = C.POINTER(C.c_double)
+    lib.qlb_generate_batch_packed.argtypes = [vp, i32, i64, vp, C.c_uint64, C.c_double, vp, vp, dp]
+    lib.qlb_generate_device.argtypes = [vp, i32, i64, vp, C.c_uint64, C.c_double, vp, vp, dp]
+    lib.qlb_run_trials.argtypes = [vp, vp, pp, i64, vp, C.c_uint64, C.c_double, vp, vp, dp]
     if path is None:
         _lib = lib
     return lib
@@ -272,6 +277,31 @@ class Context:
                          d_decoded=None, d_syndrome=None):
         _check(self.lib, self.lib.qlb_reconcile_device(self.handle, code.handle, C.byref(params), int(n_frames), d_alice, d_bob,
                                                        d_log_prior, d_iterations, d_result, d_decoded, d_syndrome))
+
+    # ---- on-device key generation (bit-exact with the reference's generator) -------------------------------------------
+    def generate(self, n_bits, seeds, qber, seed_offset=0):
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        words = (n_bits + 31) // 32
+        a = np.zeros((seeds.size, words), np.uint32)
+        b = np.zeros((seeds.size, words), np.uint32)
+        exact = C.c_double()
+        _check(self.lib, self.lib.qlb_generate_batch_packed(self.handle, int(n_bits), seeds.size, _ptr(seeds), int(seed_offset), float(qber),
+                                                            _ptr(a), _ptr(b), C.byref(exact)))
+        return a, b, exact.value
+
+    def generate_device(self, n_bits, n_frames, d_seeds, qber, d_alice, d_bob, seed_offset=0):
+        exact = C.c_double()
+        _check(self.lib, self.lib.qlb_generate_device(self.handle, int(n_bits), int(n_frames), d_seeds, int(seed_offset), float(qber),
+                                                      d_alice, d_bob, C.byref(exact)))
+        return exact.value
+
+    def run_trials(self, code: Code, params: DecodeParams, seeds, qber, seed_offset=0):
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        it, res = np.zeros(seeds.size, np.uint32), np.zeros(seeds.size, np.uint8)
+        exact = C.c_double()
+        _check(self.lib, self.lib.qlb_run_trials(self.handle, code.handle, C.byref(params), seeds.size, _ptr(seeds), int(seed_offset),
+                                                 float(qber), _ptr(it), _ptr(res), C.byref(exact)))
+        return it, res, exact.value
 
     def stats_allreduce(self, vectors, others=()):
         """In-process NCCL sum of uint64 statistics over this context and `others` (one vector per context)."""

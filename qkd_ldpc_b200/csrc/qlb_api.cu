@@ -4,6 +4,7 @@
 #include "../../include/qkd_ldpc_b200.h"
 #include "qlb_kernels.cuh"
 #include "qlb_resident_f32.cuh"
+#include "qlb_generate.cuh"
 #include "qlb_layout.hpp"
 
 #include <atomic>
@@ -94,7 +95,7 @@ struct qlb_ctx
     unsigned long long *d_counters = nullptr; // [0] frame queue, [1] executed iterations
     uint64_t launches = 0;
     std::map<uint64_t, DeviceCode> codes;
-    DevBuf scratch, in_a, in_b, in_q, in_llr, in_syn, out_it, out_res, out_dec, out_syn;
+    DevBuf scratch, in_a, in_b, in_q, in_llr, in_syn, out_it, out_res, out_dec, out_syn, gen_perm, gen_seeds;
     std::vector<double> host_logp;
     std::vector<uint32_t> host_pack_a, host_pack_b, host_pack_out;
 };
@@ -468,7 +469,7 @@ extern "C"
             for (void *p : kv.second.allocs)
                 cudaFree(p);
         for (DevBuf *b : {&ctx->scratch, &ctx->in_a, &ctx->in_b, &ctx->in_q, &ctx->in_llr, &ctx->in_syn, &ctx->out_it,
-                          &ctx->out_res, &ctx->out_dec, &ctx->out_syn})
+                          &ctx->out_res, &ctx->out_dec, &ctx->out_syn, &ctx->gen_perm, &ctx->gen_seeds})
             b->release();
         if (ctx->d_counters)
             cudaFree(ctx->d_counters);
@@ -826,6 +827,108 @@ extern "C"
             QLB_CUDA(cudaMemcpyAsync(vectors[g], ctxs[g]->in_q.p, bytes, cudaMemcpyDeviceToHost, ctxs[g]->stream));
             QLB_CUDA(cudaStreamSynchronize(ctxs[g]->stream));
         }
+        return QLB_OK;
+    }
+
+    // ---- on-device key generation -----------------------------------------------------------------------------------------
+    int qlb_generate_device(qlb_ctx *ctx, int32_t n_bits, int64_t n_frames, const uint64_t *d_seeds, uint64_t seed_offset, double qber,
+                            uint32_t *d_alice_packed_out, uint32_t *d_bob_packed_out, double *exact_qber_out)
+    {
+        if (!ctx || n_bits < 1 || n_frames < 0)
+            return fail(QLB_ERR_INVALID, "qlb_generate_device: null context, non-positive key length or negative frame count");
+        if (!(qber >= 0. && qber < 1.))
+            return fail(QLB_ERR_INVALID, "QBER must be: 0 <= QBER < 1");
+        // floor(N * q) exactly as the reference forms it (src/array_and_matrix_operations.cpp:436)
+        const size_t n_err = static_cast<size_t>(static_cast<size_t>(n_bits) * qber);
+        if (exact_qber_out)
+            *exact_qber_out = static_cast<double>(n_err) / static_cast<size_t>(n_bits);
+        if (n_err == 0)
+            return fail(QLB_ERR_KEY_TOO_SMALL, "Key size '" + std::to_string(n_bits) + "' is too small for QBER.");
+        if (n_frames == 0)
+            return QLB_OK;
+        if (!d_seeds || !d_alice_packed_out || !d_bob_packed_out)
+            return fail(QLB_ERR_INVALID, "qlb_generate_device: null device buffer");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const int words = (n_bits + 31) / 32;
+        const size_t pos_bytes = n_bits <= 65536 ? 2 : 4;
+        // bound the shuffle scratch: process the batch in slices
+        const int64_t slice = std::max<int64_t>(1, std::min<int64_t>(n_frames, (int64_t)((1ull << 30) / ((size_t)n_bits * pos_bytes))));
+        QLB_CUDA(ctx->gen_perm.reserve((size_t)slice * n_bits * pos_bytes));
+        for (int64_t f0 = 0; f0 < n_frames; f0 += slice)
+        {
+            const int64_t nf = std::min(slice, n_frames - f0);
+            const unsigned grid = (unsigned)((nf + 127) / 128);
+            if (pos_bytes == 2)
+                generate_keys_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(nf, n_bits, words, (long long)n_err, d_seeds + f0, seed_offset,
+                                                                              (uint16_t *)ctx->gen_perm.p, d_alice_packed_out + f0 * words,
+                                                                              d_bob_packed_out + f0 * words);
+            else
+                generate_keys_kernel<uint32_t><<<grid, 128, 0, ctx->stream>>>(nf, n_bits, words, (long long)n_err, d_seeds + f0, seed_offset,
+                                                                              (uint32_t *)ctx->gen_perm.p, d_alice_packed_out + f0 * words,
+                                                                              d_bob_packed_out + f0 * words);
+            QLB_CUDA(cudaGetLastError());
+        }
+        return QLB_OK;
+    }
+
+    int qlb_generate_batch_packed(qlb_ctx *ctx, int32_t n_bits, int64_t n_frames, const uint64_t *seeds, uint64_t seed_offset, double qber,
+                                  uint32_t *alice_packed_out, uint32_t *bob_packed_out, double *exact_qber_out)
+    {
+        if (!ctx || n_bits < 1 || n_frames < 0 || (n_frames > 0 && (!seeds || !alice_packed_out || !bob_packed_out)))
+            return fail(QLB_ERR_INVALID, "qlb_generate_batch_packed: bad arguments");
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const size_t key_bytes = (size_t)n_frames * ((n_bits + 31) / 32) * 4;
+        QLB_CUDA(ctx->gen_seeds.reserve((size_t)n_frames * 8 + 8));
+        QLB_CUDA(ctx->in_a.reserve(key_bytes + 4));
+        QLB_CUDA(ctx->in_b.reserve(key_bytes + 4));
+        if (n_frames)
+            QLB_CUDA(cudaMemcpyAsync(ctx->gen_seeds.p, seeds, (size_t)n_frames * 8, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = qlb_generate_device(ctx, n_bits, n_frames, (const uint64_t *)ctx->gen_seeds.p, seed_offset, qber, (uint32_t *)ctx->in_a.p,
+                                     (uint32_t *)ctx->in_b.p, exact_qber_out);
+        if (rc || n_frames == 0)
+            return rc;
+        QLB_CUDA(cudaMemcpyAsync(alice_packed_out, ctx->in_a.p, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(bob_packed_out, ctx->in_b.p, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return QLB_OK;
+    }
+
+    int qlb_run_trials(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames, const uint64_t *seeds,
+                       uint64_t seed_offset, double qber, uint32_t *iterations_out, uint8_t *result_out, double *exact_qber_out)
+    {
+        if (!ctx || !code || n_frames < 0 || (n_frames > 0 && (!seeds || !iterations_out || !result_out)))
+            return fail(QLB_ERR_INVALID, "qlb_run_trials: bad arguments");
+        int rc = check_params(params);
+        if (rc)
+            return rc;
+        const CodeLayout &L = code->L;
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const size_t key_bytes = (size_t)n_frames * L.words_n * 4;
+        QLB_CUDA(ctx->gen_seeds.reserve((size_t)n_frames * 8 + 8));
+        QLB_CUDA(ctx->in_a.reserve(key_bytes + 4));
+        QLB_CUDA(ctx->in_b.reserve(key_bytes + 4));
+        QLB_CUDA(ctx->in_q.reserve((size_t)n_frames * 8 + 8));
+        QLB_CUDA(ctx->out_it.reserve((size_t)n_frames * 4 + 4));
+        QLB_CUDA(ctx->out_res.reserve((size_t)n_frames + 4));
+        if (n_frames)
+            QLB_CUDA(cudaMemcpyAsync(ctx->gen_seeds.p, seeds, (size_t)n_frames * 8, cudaMemcpyHostToDevice, ctx->stream));
+        double exact = 0.;
+        rc = qlb_generate_device(ctx, L.n, n_frames, (const uint64_t *)ctx->gen_seeds.p, seed_offset, qber, (uint32_t *)ctx->in_a.p,
+                                 (uint32_t *)ctx->in_b.p, &exact);
+        if (exact_qber_out)
+            *exact_qber_out = exact;
+        if (rc || n_frames == 0)
+            return rc;
+        // ln((1-q)/q) of the exact ratio, on the host in double as the reference forms it (src/qkd_ldpc_algorithm.cpp:400)
+        ctx->host_logp.assign((size_t)n_frames, std::log((1. - exact) / exact));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_q.p, ctx->host_logp.data(), (size_t)n_frames * 8, cudaMemcpyHostToDevice, ctx->stream));
+        rc = qlb_reconcile_device(ctx, code, params, n_frames, (const uint32_t *)ctx->in_a.p, (const uint32_t *)ctx->in_b.p, (const double *)ctx->in_q.p,
+                                  (uint32_t *)ctx->out_it.p, (uint8_t *)ctx->out_res.p, nullptr, nullptr);
+        if (rc)
+            return rc;
+        QLB_CUDA(cudaMemcpyAsync(iterations_out, ctx->out_it.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(result_out, ctx->out_res.p, (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
         return QLB_OK;
     }
 }

@@ -81,6 +81,8 @@ config_data get_config_data(fs::path config_path)
             cfg.DEVICE_FP32_FAST = root.at("device_fp32_fast_math").as_bool();
         if (root.contains("device_gpus"))
             cfg.DEVICE_GPUS = static_cast<int>(root.at("device_gpus").as_size());
+        if (root.contains("device_generate_keys"))
+            cfg.DEVICE_GENERATE_KEYS = root.at("device_generate_keys").as_bool();
         if (root.contains("device_batch_frames"))
         {
             cfg.DEVICE_BATCH_FRAMES = root.at("device_batch_frames").as_size();

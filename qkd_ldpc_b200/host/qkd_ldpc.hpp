@@ -74,6 +74,8 @@ struct config_data
     bool DEVICE_FP32_FAST = false; // "device_fp32_fast_math": SFU check rule for fp32
     int DEVICE_GPUS = 0;           // "device_gpus": 0 = all visible GPUs
     size_t DEVICE_BATCH_FRAMES = 4096; // "device_batch_frames": frames per launch handed to one GPU
+    bool DEVICE_GENERATE_KEYS = true;  // "device_generate_keys": draw Alice/Bob on the GPU from the trial seeds (bit-exact with
+                                       // generate_random_bit_array / introduce_errors); false = host threads generate
 };
 
 extern config_data CFG;

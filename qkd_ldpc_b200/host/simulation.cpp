@@ -84,6 +84,9 @@ namespace
     struct batch
     {
         size_t first_trial = 0, frames = 0;
+        bool on_device = false;           // keys are generated on the GPU from seeds[first_trial ...] + seed_offset
+        uint64_t seed_offset = 0;
+        double requested_qber = 0;
         std::vector<uint32_t> alice, bob; // packed keys
         std::vector<double> qber;         // exact QBER per frame
         std::vector<uint32_t> iterations;
@@ -244,15 +247,17 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
 
     worker_pool generators(CFG.THREADS_NUMBER);
     const size_t gen_parts = std::max<size_t>(1, CFG.THREADS_NUMBER);
-    std::vector<batch> pool(static_cast<size_t>(gpus) * 2 + 1);
+    // two host threads (and contexts/streams) per GPU: one batch's key generation and transfers overlap another's decode
+    const int workers_per_gpu = 2, workers = gpus * workers_per_gpu;
+    std::vector<batch> pool(static_cast<size_t>(workers) * 2 + 1);
     batch_queue free_batches, ready;
     for (batch &b : pool)
         free_batches.push(&b);
 
     // ---- GPU workers: one host thread + one context per GPU ---------------------------------------------------------
     std::vector<trial_result> trial_results(trials);
-    std::vector<std::vector<uint64_t>> gpu_stats(gpus, std::vector<uint64_t>(stats_width, 0));
-    std::vector<qlb_ctx *> contexts(gpus, nullptr);
+    std::vector<std::vector<uint64_t>> gpu_stats(workers, std::vector<uint64_t>(stats_width, 0)); // per worker, folded per GPU below
+    std::vector<qlb_ctx *> contexts(workers, nullptr);
     std::atomic<size_t> batches_done{0};
     std::mutex err_mu, done_mu;
     std::condition_variable done_cv;
@@ -260,10 +265,10 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     qlb_code *code = nullptr;                 // the current matrix
     std::atomic<uint64_t> device_ns{0};
     std::vector<std::thread> gpu_threads;
-    for (int g = 0; g < gpus; ++g)
+    for (int g = 0; g < workers; ++g)
         gpu_threads.emplace_back([&, g]
                                  {
-            try { contexts[g] = qkd_b200::context(g); }
+            try { contexts[g] = qkd_b200::context(g % gpus); } // worker g drives GPU g % gpus with its own context
             catch (const std::exception &e) { std::lock_guard<std::mutex> lk(err_mu); if (first_error.empty()) first_error = e.what(); }
             for (;;)
             {
@@ -273,14 +278,23 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 if (contexts[g] && first_error.empty())
                 {
                     const auto t0 = clock::now();
-                    const int rc = qlb_reconcile_batch_packed(contexts[g], code, &params, static_cast<int64_t>(b->frames), b->alice.data(), b->bob.data(),
-                                                              b->qber.data(), b->iterations.data(), b->result.data(), nullptr, nullptr);
+                    int rc;
+                    if (b->on_device)
+                    {
+                        double exact = 0;
+                        rc = qlb_run_trials(contexts[g], code, &params, static_cast<int64_t>(b->frames), reinterpret_cast<const uint64_t *>(&seeds[b->first_trial]),
+                                            b->seed_offset, b->requested_qber, b->iterations.data(), b->result.data(), &exact);
+                        std::fill(b->qber.begin(), b->qber.end(), exact);
+                    }
+                    else
+                        rc = qlb_reconcile_batch_packed(contexts[g], code, &params, static_cast<int64_t>(b->frames), b->alice.data(), b->bob.data(),
+                                                        b->qber.data(), b->iterations.data(), b->result.data(), nullptr, nullptr);
                     device_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(clock::now() - t0).count();
                     if (rc != QLB_OK)
                     {
                         std::lock_guard<std::mutex> lk(err_mu);
                         if (first_error.empty())
-                            first_error = std::string("qlb_reconcile_batch_packed: ") + qlb_last_error();
+                            first_error = qlb_last_error();
                     }
                     else
                     {
@@ -312,7 +326,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
             } });
     auto shut_down = [&]
     {
-        for (int g = 0; g < gpus; ++g)
+        for (int g = 0; g < workers; ++g)
             ready.push(nullptr);
         for (auto &t : gpu_threads)
             t.join();
@@ -341,11 +355,19 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                     batch *b = free_batches.pop();
                     b->first_trial = first;
                     b->frames = std::min(batch_frames, trials - first);
-                    b->alice.resize(b->frames * words);
-                    b->bob.resize(b->frames * words);
                     b->qber.resize(b->frames);
                     b->iterations.resize(b->frames);
                     b->result.resize(b->frames);
+                    b->on_device = CFG.DEVICE_GENERATE_KEYS;
+                    b->seed_offset = curr_sim;
+                    b->requested_qber = QBER;
+                    if (b->on_device)
+                    {
+                        ready.push(b); // nothing to prepare on the host: the trial seeds are the input
+                        continue;
+                    }
+                    b->alice.resize(b->frames * words);
+                    b->bob.resize(b->frames * words);
                     const size_t parts = std::min(gen_parts, b->frames);
                     b->parts_left = parts;
                     for (size_t part = 0; part < parts; ++part)
@@ -366,12 +388,15 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                     throw std::runtime_error(first_error);
 
                 // the sweep's one collective: sum the per-GPU integer statistics (NCCL all-reduce over the GPUs of this box)
+                for (int w = gpus; w < workers; ++w) // fold the second worker of each GPU into the first
+                    for (size_t x = 0; x < stats_width; ++x)
+                        gpu_stats[w % gpus][x] += gpu_stats[w][x];
                 std::vector<uint64_t> reduced = gpu_stats[0];
                 if (gpus > 1 || std::getenv("QKD_B200_FORCE_ALLREDUCE"))
                 {
                     std::vector<uint64_t *> ptrs;
-                    for (auto &st : gpu_stats)
-                        ptrs.push_back(st.data());
+                    for (int g = 0; g < gpus; ++g)
+                        ptrs.push_back(gpu_stats[g].data());
                     qkd_b200::check(qlb_stats_allreduce(contexts.data(), gpus, ptrs.data(), stats_width), "qlb_stats_allreduce");
                     reduced = gpu_stats[0];
                 }
@@ -427,7 +452,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     shut_down();
 
     g_report.seconds_total = std::chrono::duration<double>(clock::now() - t_start).count();
-    g_report.seconds_device = device_ns.load() * 1e-9 / gpus;
+    g_report.seconds_device = device_ns.load() * 1e-9 / workers;
     g_report.frames = frames_total;
     g_report.frame_iterations = iterations_total;
     g_report.gpus = gpus;

@@ -229,3 +229,32 @@ def test_edge_cases(ctx, dev_codes, graphs, oracle, frames):
     with pytest.raises(capi.QlbError) as ei:
         ctx.reconcile_packed(code, p, a, b, np.array([0.0]))
     assert "too small for QBER" in str(ei.value)
+
+
+@pytest.mark.parametrize("n,q", [(10240, 0.03), (10240, 0.11), (7, 0.15), (7, 0.3), (6, 0.2), (33, 0.25), (100, 0.5), (70000, 0.01)])
+def test_device_generator_bit_exact(ctx, oracle, n, q):
+    """qlb_generate_batch_packed reproduces the reference's keys (xoshiro256++ stream, libstdc++ bit draw and shuffle)."""
+    seeds = oracle.trial_seeds(777, 6) if n < 70000 else oracle.trial_seeds(5, 2)
+    for off in (0, 3):
+        a, b, exact = ctx.generate(n, seeds, q, seed_offset=off)
+        for k, s in enumerate(seeds):
+            wa, wb, wex = oracle.generate(int(s) + off & 0xFFFFFFFFFFFFFFFF, n, q)
+            assert exact == wex
+            assert (capi.unpack_bits(a[k:k + 1], n)[0] == wa).all(), (n, q, k)
+            assert (capi.unpack_bits(b[k:k + 1], n)[0] == wb).all(), (n, q, k)
+            assert int((wa != wb).sum()) == int(n * q)
+    with pytest.raises(capi.QlbError) as ei:
+        ctx.generate(n, seeds, 0.5 / n)
+    assert "too small for QBER" in str(ei.value)
+
+
+def test_run_trials_equals_reference_trials(ctx, dev_codes, graphs, oracle):
+    """qlb_run_trials (keys generated on the device from trial seeds, then reconciled) == the reference's run_trial."""
+    g, code = graphs[NS], dev_codes[NS]
+    seeds = oracle.trial_seeds(777, 32)
+    p = capi.make_params(64, 100, 100.0, True)
+    for pt, q in enumerate([0.03, 0.08, 0.09]):
+        want = oracle.run_trials(g, q, seeds + np.uint64(pt), threads=8)
+        it, res, exact = ctx.run_trials(code, p, seeds, q, seed_offset=pt)
+        assert exact == int(g.n * q) / g.n
+        assert (it == want[:, 0]).all() and ((res & 1) == want[:, 1]).all() and (((res >> 1) & 1) == want[:, 2]).all()

@@ -116,10 +116,12 @@ def test_cpp_no_gpu_fails_loudly(sim, tmp_path, lib):
 
 
 @pytest.mark.gpu
-def test_sweep_csv_equals_reference_north_star(sim, tmp_path):
+@pytest.mark.parametrize("device_keys", [True, False])
+def test_sweep_csv_equals_reference_north_star(sim, tmp_path, device_keys):
     """config.json -> CSV on the N=10240 code, 64 trials x 9 QBER points: byte-identical to the CSV written by the
-    reference's own main() (tests/golden/sweep_n10240_t64_seed777.csv), fp64 messages."""
-    d = make_dir(tmp_path, base_cfg(), NS, False)
+    reference's own main() (tests/golden/sweep_n10240_t64_seed777.csv), fp64 messages; keys drawn on the GPU from the
+    trial seeds (default) or by host threads."""
+    d = make_dir(tmp_path, base_cfg(device_generate_keys=device_keys), NS, False)
     run(sim, d)
     out = sorted((d / "results").glob("*.csv"))
     assert len(out) == 1 and out[0].name == "ldpc(trial_num=64,max_sum_prod_iters=100,seed=777).csv"
