@@ -5,6 +5,7 @@
 #include "qlb_kernels.cuh"
 #include "qlb_resident_f32.cuh"
 #include "qlb_generate.cuh"
+#include "qlb_stream_f32.cuh"
 #include "qlb_layout.hpp"
 
 #include <atomic>
@@ -266,6 +267,56 @@ namespace
                resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) + kResidentStaticSmem <= (size_t)ctx->smem_optin;
     }
 
+    // The frame-interleaved streaming kernel (qlb_stream_f32.cuh): messages in HBM, any block length.
+    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    int launch_stream(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        auto kern = decode_stream_f32_kernel<Rule, kReconcile, kBW, VEC>;
+        const StreamCarve cv = stream_carve(args.code.n, args.code.m, args.code.slots, VEC);
+        const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
+        long long grid = ctx->sm_count; // one resident CTA per SM
+        if (grid > groups)
+            grid = groups;
+        QLB_CUDA(ctx->scratch.reserve((size_t)grid * cv.total));
+        if (args.syndrome_out)
+            QLB_CUDA(cudaMemsetAsync(args.syndrome_out, 0, (size_t)args.n_frames * args.code.words_m * 4, ctx->stream));
+        if (std::getenv("QLB_DEBUG"))
+            std::fprintf(stderr, "[qlb] decode_stream_f32_kernel VEC=%d: %lld groups of %lld frames, grid=%lld, %zu B scratch per group\n", VEC,
+                         groups, G, grid, cv.total);
+        QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+        args.queue = ctx->d_counters;
+        args.iter_total = ctx->d_counters + 1;
+        kern<<<(unsigned)grid, kStreamThreads, 0, ctx->stream>>>(args, static_cast<unsigned char *>(ctx->scratch.p), cv.total, groups);
+        QLB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+        return QLB_OK;
+    }
+
+    template <typename Rule, bool kReconcile>
+    int launch_stream_bw(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        // 128-bit accesses (128 frames per group) unless the per-SM message arrays would not fit in device memory
+        size_t free_b = 0, total_b = 0;
+        QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need4 = (size_t)ctx->sm_count * stream_carve(args.code.n, args.code.m, args.code.slots, 4).total;
+        const bool vec4 = need4 <= (free_b + ctx->scratch.cap) / 10 * 7 && args.n_frames > 32;
+        switch (args.code.uniform_bit_w * 10 + (vec4 ? 4 : 1))
+        {
+        case 24: return launch_stream<Rule, kReconcile, 2, 4>(ctx, args);
+        case 34: return launch_stream<Rule, kReconcile, 3, 4>(ctx, args);
+        case 44: return launch_stream<Rule, kReconcile, 4, 4>(ctx, args);
+        case 21: return launch_stream<Rule, kReconcile, 2, 1>(ctx, args);
+        case 31: return launch_stream<Rule, kReconcile, 3, 1>(ctx, args);
+        case 41: return launch_stream<Rule, kReconcile, 4, 1>(ctx, args);
+        default: return fail(QLB_ERR_UNSUPPORTED, "streaming kernel: unsupported bit weight");
+        }
+    }
+
+    bool stream_eligible(const CodeDev &c)
+    {
+        return c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW && c.m <= c.n;
+    }
+
     template <typename Math, bool kReconcile>
     int launch_tier(qlb_ctx *ctx, DecodeArgs &args, int forced_tier)
     {
@@ -305,6 +356,15 @@ namespace
                 return launch_resident_bw<RuleF32Fast, kReconcile>(ctx, args);
             return launch_resident_bw<RuleF32Accurate, kReconcile>(ctx, args);
         }
+        // codes too large for one SM's shared memory: frame-interleaved streaming through HBM (test hook: tier 3 forces it)
+        if (p->precision == QLB_PRECISION_F32 && (forced < 0 || forced == 3) && stream_eligible(args.code))
+        {
+            if (p->flags & QLB_FLAG_F32_FAST_MATH)
+                return launch_stream_bw<RuleF32Fast, kReconcile>(ctx, args);
+            return launch_stream_bw<RuleF32Accurate, kReconcile>(ctx, args);
+        }
+        if (forced == 3)
+            return fail(QLB_ERR_UNSUPPORTED, "the streaming kernel does not handle this code / precision");
         if (p->precision == QLB_PRECISION_F64)
             return launch_tier<MathF64, kReconcile>(ctx, args, forced);
         if (p->flags & QLB_FLAG_F32_FAST_MATH)

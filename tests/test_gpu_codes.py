@@ -61,3 +61,50 @@ def test_large_block_length_matches_oracle(ctx, oracle):
             if precision == 64:
                 assert (it == want[:, 0]).all()
                 assert (capi.unpack_bits(dec, n) == wdec).all()
+
+
+def test_streaming_kernel_equals_resident_kernel(ctx, oracle):
+    """The frame-interleaved HBM-streaming kernel (forced with the tier-3 test hook) runs the same node arithmetic as the
+    SM-resident kernel: iterations, flags and decoded keys must be identical, for a ragged batch (300 frames = 2 groups + 44)
+    mixing QBER points, in both fp32 rules."""
+    mat = codes.load_npz(codes.NORTH_STAR)
+    code = capi.Code.from_graph(mat)
+    seeds = oracle.trial_seeds(31337, 300)
+    qs = [0.03, 0.07, 0.085, 0.09]
+    A, B, Q = [], [], []
+    for k, s in enumerate(seeds):
+        a, b, ex = oracle.generate(int(s), mat.n, qs[k % 4])
+        A.append(a); B.append(b); Q.append(ex)
+    A, B, Q = capi.pack_bits(np.stack(A)), capi.pack_bits(np.stack(B)), np.array(Q)
+    for fast in (True, False):
+        r = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=fast), A, B, Q, want_syndrome=True)
+        s = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=fast, tier=3), A, B, Q, want_syndrome=True)
+        assert (r[0] == s[0]).all(), np.flatnonzero(r[0] != s[0])
+        assert (r[1] == s[1]).all() and (r[2] == s[2]).all() and (r[3] == s[3]).all()
+    # and the sum-product entry (arbitrary LLRs + target syndromes) through the streaming kernel
+    g = graph_of(mat)
+    bob = capi.unpack_bits(B[:5], mat.n); alice = capi.unpack_bits(A[:5], mat.n)
+    llr = np.where(bob != 0, -1.0, 1.0) * np.log((1 - Q[:5]) / Q[:5])[:, None]
+    syn = np.stack([oracle.syndrome(g, a) for a in alice])
+    it_r, res_r, bits_r = ctx.sum_product(code, capi.make_params(32, 60, 100.0, True, fast_math=True), llr, syn)
+    it_s, res_s, bits_s = ctx.sum_product(code, capi.make_params(32, 60, 100.0, True, fast_math=True, tier=3), llr, syn)
+    assert (it_r == it_s).all() and (res_r == res_s).all() and (bits_r == bits_s).all()
+
+
+def test_streaming_kernel_large_block_length(ctx, oracle):
+    """N = 100 000 in fp32 goes through the streaming kernel by default; flags must equal the fp64 oracle's."""
+    n, m = 100000, 51080
+    mat = codes.peg_code(n, m, 3, 666, bfs_limit=2000)
+    g, code = graph_of(mat), capi.Code.from_graph(mat)
+    seeds = oracle.trial_seeds(99, 3)
+    for q, mi in ((0.05, 100), (0.10, 12)):
+        want, wdec = oracle.run_trials(g, q, seeds, threads=3, max_it=mi, want_decoded=True)
+        A, B, Q = frames_for(oracle, n, q, seeds)
+        for fast in (True, False):
+            it, res, dec, syn = ctx.reconcile_packed(code, capi.make_params(32, mi, 100.0, True, fast_math=fast), capi.pack_bits(A), capi.pack_bits(B), Q,
+                                                     want_syndrome=True)
+            assert (capi.unpack_bits(syn, m) == np.stack([oracle.syndrome(g, a) for a in A])).all()
+            assert ((res & 1) == want[:, 1]).all() and (((res >> 1) & 1) == want[:, 2]).all()
+            ok = want[:, 1] == 1
+            assert (capi.unpack_bits(dec, n)[ok] == wdec[ok]).all()
+            assert (np.abs(it.astype(int) - want[:, 0].astype(int)) <= 1).all()
