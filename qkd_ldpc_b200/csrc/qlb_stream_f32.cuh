@@ -17,6 +17,7 @@
 namespace qlb
 {
     constexpr int kStreamThreads = 512;
+    constexpr int kPrefetchAhead = 2; // nodes ahead (per warp) whose message rows are prefetched into L2
 
     template <int VEC>
     struct VecIO;
@@ -39,6 +40,11 @@ namespace qlb
         static __device__ __forceinline__ void load(const float *p, float (&v)[1]) { v[0] = *p; }
         static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
     };
+
+    // Software prefetch into L2: registers bound how many demand loads a warp can keep in flight (W rows of 512 B), which is
+    // not enough to cover HBM latency at 16 warps per SM; prefetching the NEXT node's rows costs no registers and turns the
+    // demand loads that follow into L2 hits.
+    __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
     // per-group scratch carve-up (bytes); G = 32 * VEC
     struct StreamCarve
@@ -134,7 +140,12 @@ namespace qlb
 #define QLB_SSEG(W_)                                                                    \
     case W_:                                                                            \
         _Pragma("unroll 1") for (uint32_t p = lo + warp; p < hi; p += nwarps)           \
+        {                                                                               \
+            if (p + kPrefetchAhead * nwarps < hi)                                       \
+                _Pragma("unroll") for (int k = 0; k < W_; ++k)                          \
+                    prefetch_l2(msg + ((size_t)(code.base[k] + p + kPrefetchAhead * nwarps) * (32 * VEC) + VEC * lane)); \
             stream_check<Rule, W_, VEC>(msg, code, p, lane, synT, cap, first, bad);     \
+        }                                                                               \
         break;
                 QLB_SSEG(1) QLB_SSEG(2) QLB_SSEG(3) QLB_SSEG(4) QLB_SSEG(5) QLB_SSEG(6) QLB_SSEG(7) QLB_SSEG(8)
                 QLB_SSEG(9) QLB_SSEG(10) QLB_SSEG(11) QLB_SSEG(12) QLB_SSEG(13) QLB_SSEG(14) QLB_SSEG(15) QLB_SSEG(16)
@@ -363,6 +374,10 @@ namespace qlb
                     act_word[j] = __ballot_sync(0xffffffffu, (active >> j) & 1u);
                 for (int i = warp; i < n; i += kWarps)
                 {
+                    if (i + kPrefetchAhead * kWarps < n)
+#pragma unroll
+                        for (int a = 0; a < kBW; ++a)
+                            prefetch_l2(msg + ((size_t)code.bit_slots32[(size_t)a * n + i + kPrefetchAhead * kWarps] * G + VEC * lane));
                     float *row[kBW];
                     float c[kBW][VEC];
 #pragma unroll
