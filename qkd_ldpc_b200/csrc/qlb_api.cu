@@ -268,10 +268,12 @@ namespace
     }
 
     // The frame-interleaved streaming kernel (qlb_stream_f32.cuh): messages in HBM, any block length.
-    template <typename Rule, bool kReconcile, int kBW, int VEC>
-    int launch_stream(qlb_ctx *ctx, DecodeArgs &args)
+    template <typename Rule, bool kReconcile, int kBW, int VEC, bool kTma>
+    int launch_stream(qlb_ctx *ctx, DecodeArgs &args, int stages)
     {
-        auto kern = decode_stream_f32_kernel<Rule, kReconcile, kBW, VEC>;
+        auto kern = decode_stream_f32_kernel<Rule, kReconcile, kBW, VEC, kTma>;
+        const size_t ring = kTma ? (size_t)(kStreamThreads / 32) * stages * ((size_t)std::max(args.code.max_check_w, kBW) * 128 * VEC + 8) + 128 : 0;
+        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
         const StreamCarve cv = stream_carve(args.code.n, args.code.m, args.code.slots, VEC);
         const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
         long long grid = ctx->sm_count; // one resident CTA per SM
@@ -281,12 +283,14 @@ namespace
         if (args.syndrome_out)
             QLB_CUDA(cudaMemsetAsync(args.syndrome_out, 0, (size_t)args.n_frames * args.code.words_m * 4, ctx->stream));
         if (std::getenv("QLB_DEBUG"))
-            std::fprintf(stderr, "[qlb] decode_stream_f32_kernel VEC=%d: %lld groups of %lld frames, grid=%lld, %zu B scratch per group\n", VEC,
-                         groups, G, grid, cv.total);
+            std::fprintf(stderr, "[qlb] decode_stream_f32_kernel VEC=%d tma=%d stages=%d ring=%zu B: %lld groups of %lld frames, grid=%lld, %zu B scratch per group\n",
+                         VEC, (int)kTma, stages, ring, groups, G, grid, cv.total);
         QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;
-        kern<<<(unsigned)grid, kStreamThreads, 0, ctx->stream>>>(args, static_cast<unsigned char *>(ctx->scratch.p), cv.total, groups);
+        const char *pf = std::getenv("QLB_STREAM_PREFETCH"); // nodes ahead (per warp) whose rows are prefetched into L2
+        kern<<<(unsigned)grid, kStreamThreads, ring, ctx->stream>>>(args, static_cast<unsigned char *>(ctx->scratch.p), cv.total, groups,
+                                                                    pf ? std::atoi(pf) : 4, stages);
         QLB_CUDA(cudaGetLastError());
         ++ctx->launches;
         return QLB_OK;
@@ -300,14 +304,22 @@ namespace
         QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t need4 = (size_t)ctx->sm_count * stream_carve(args.code.n, args.code.m, args.code.slots, 4).total;
         const bool vec4 = need4 <= (free_b + ctx->scratch.cap) / 10 * 7 && args.n_frames > 32;
+        // TMA rings: 16 warps x S stages x (rows x row bytes) of shared memory; needs S >= 3 and check weights <= 8
+        const size_t stage_bytes = (size_t)std::max(args.code.max_check_w, args.code.uniform_bit_w) * 128 * (vec4 ? 4 : 1) + 8;
+        int stages = (int)std::min<size_t>(8, ((size_t)ctx->smem_optin - 4096) / ((kStreamThreads / 32) * stage_bytes));
+        // Measured on B200 (N = 100 000, 18 944 frames): per-warp TMA rings of 512-byte bulk copies reach 0.49 of the HBM copy
+        // bandwidth, plain 128-bit loads + L2 software prefetch 0.57-0.58 -- the rings are kept as an opt-in experiment.
+        const bool tma = stages >= 3 && args.code.max_check_w <= 8 && args.code.uniform_bit_w == 3 && std::getenv("QLB_STREAM_TMA");
+        if (tma)
+            return vec4 ? launch_stream<Rule, kReconcile, 3, 4, true>(ctx, args, stages) : launch_stream<Rule, kReconcile, 3, 1, true>(ctx, args, stages);
         switch (args.code.uniform_bit_w * 10 + (vec4 ? 4 : 1))
         {
-        case 24: return launch_stream<Rule, kReconcile, 2, 4>(ctx, args);
-        case 34: return launch_stream<Rule, kReconcile, 3, 4>(ctx, args);
-        case 44: return launch_stream<Rule, kReconcile, 4, 4>(ctx, args);
-        case 21: return launch_stream<Rule, kReconcile, 2, 1>(ctx, args);
-        case 31: return launch_stream<Rule, kReconcile, 3, 1>(ctx, args);
-        case 41: return launch_stream<Rule, kReconcile, 4, 1>(ctx, args);
+        case 24: return launch_stream<Rule, kReconcile, 2, 4, false>(ctx, args, 0);
+        case 34: return launch_stream<Rule, kReconcile, 3, 4, false>(ctx, args, 0);
+        case 44: return launch_stream<Rule, kReconcile, 4, 4, false>(ctx, args, 0);
+        case 21: return launch_stream<Rule, kReconcile, 2, 1, false>(ctx, args, 0);
+        case 31: return launch_stream<Rule, kReconcile, 3, 1, false>(ctx, args, 0);
+        case 41: return launch_stream<Rule, kReconcile, 4, 1, false>(ctx, args, 0);
         default: return fail(QLB_ERR_UNSUPPORTED, "streaming kernel: unsupported bit weight");
         }
     }

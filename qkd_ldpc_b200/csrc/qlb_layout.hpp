@@ -55,7 +55,9 @@ namespace qlb
         {
             const int32_t warps = (n + 31) / 32;
             const int32_t groups = warps * max_bit_w;
-            if (m < 64 || groups <= 0)
+            // Only codes that can live in shared memory profit (slots < 65535 is the resident kernels' limit); for larger codes
+            // the natural order keeps the first edges of consecutive bits on consecutive message rows (DRAM locality).
+            if (m < 64 || groups <= 0 || e >= 65535 || std::getenv("QLB_NO_BANK_SPREAD"))
                 return;
             // groups a check belongs to (one per edge): (warp of the bit, position of this edge in the bit's list)
             std::vector<std::vector<int32_t>> groups_of(m);

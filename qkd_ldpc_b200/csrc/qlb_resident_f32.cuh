@@ -69,6 +69,19 @@ namespace qlb
                      : "memory");
     }
 
+    __device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+    {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+    template <int N>
+    __device__ __forceinline__ void bulk_wait_read()
+    {
+        asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+    }
+    __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
     // ---- check rules for a check of weight exactly W -------------------------------------------------------------------
     // v[] holds the raw incoming messages and receives the outgoing ones. xr = XOR of the raw message words, with the
     // check's syndrome bit folded into bit 31 (sign of the seeded product, src/qkd_ldpc_algorithm.cpp:231).

@@ -17,7 +17,6 @@
 namespace qlb
 {
     constexpr int kStreamThreads = 512;
-    constexpr int kPrefetchAhead = 2; // nodes ahead (per warp) whose message rows are prefetched into L2
 
     template <int VEC>
     struct VecIO;
@@ -125,7 +124,7 @@ namespace qlb
     template <typename Rule, int VEC>
     __device__ __forceinline__ void stream_check_pass(float *__restrict__ msg, const CodeDev &code, const uint32_t *s_seg_w, const uint32_t *s_seg_lo,
                                                       const uint32_t *s_seg_hi, int nseg, uint32_t *__restrict__ synT, float cap, bool first,
-                                                      uint32_t (&bad)[VEC])
+                                                      uint32_t ahead, uint32_t (&bad)[VEC])
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
@@ -141,9 +140,9 @@ namespace qlb
     case W_:                                                                            \
         _Pragma("unroll 1") for (uint32_t p = lo + warp; p < hi; p += nwarps)           \
         {                                                                               \
-            if (p + kPrefetchAhead * nwarps < hi)                                       \
+            if (p + ahead < hi)                                                         \
                 _Pragma("unroll") for (int k = 0; k < W_; ++k)                          \
-                    prefetch_l2(msg + ((size_t)(code.base[k] + p + kPrefetchAhead * nwarps) * (32 * VEC) + VEC * lane)); \
+                    prefetch_l2(msg + ((size_t)(code.base[k] + p + ahead) * (32 * VEC) + VEC * lane)); \
             stream_check<Rule, W_, VEC>(msg, code, p, lane, synT, cap, first, bad);     \
         }                                                                               \
         break;
@@ -215,13 +214,32 @@ namespace qlb
         }
     }
 
-    // Requirements (host-checked): max_check_w <= 16, uniform bit weight kBW. Grid: persistent, one group per CTA at a time.
-    template <typename Rule, bool kReconcile, int kBW, int VEC>
+}
+#include "qlb_stream_tma.cuh"
+namespace qlb
+{
+    // Requirements (host-checked): max_check_w <= 16 (<= 8 for kTma), uniform bit weight kBW. Grid: persistent, one group per
+    // CTA at a time. kTma: the passes run through per-warp TMA rings in dynamic shared memory (`stages` per warp).
+    template <typename Rule, bool kReconcile, int kBW, int VEC, bool kTma>
     __global__ void __launch_bounds__(kStreamThreads, 1) decode_stream_f32_kernel(const DecodeArgs args, unsigned char *__restrict__ group_scratch,
-                                                                                  size_t group_stride, long long n_groups)
+                                                                                  size_t group_stride, long long n_groups, int prefetch_nodes, int stages)
     {
         constexpr int G = 32 * VEC;
         constexpr int kWarps = kStreamThreads / 32;
+        const int ahead = prefetch_nodes * kWarps; // this warp's node `prefetch_nodes` steps ahead
+        extern __shared__ __align__(128) unsigned char ring_smem[];
+        WarpPipe pp{};
+        if (kTma)
+        {
+            const uint32_t rows = (uint32_t)max(args.code.max_check_w, kBW);
+            pp.stage_bytes = rows * 4u * G;
+            pp.S = stages;
+            pp.stages = ring_smem + (size_t)(threadIdx.x >> 5) * stages * pp.stage_bytes;
+            pp.bars = reinterpret_cast<uint64_t *>(ring_smem + (size_t)kWarps * stages * pp.stage_bytes) + (size_t)(threadIdx.x >> 5) * stages;
+            if ((threadIdx.x & 31) == 0)
+                for (int s = 0; s < stages; ++s)
+                    mbar_init(&pp.bars[s], 1);
+        }
         __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
         __shared__ uint32_t s_flags[kWarps][32];
         __shared__ int s_nseg;
@@ -342,7 +360,10 @@ namespace qlb
             for (;;)
             {
                 uint32_t bad[VEC];
-                stream_check_pass<Rule, VEC>(msg, code, s_seg_w, s_seg_lo, s_seg_hi, nseg, synT, cap, kReconcile && it == 0, bad);
+                if constexpr (kTma)
+                    tma_check_pass<Rule, VEC>(msg, code, s_seg_w, s_seg_lo, s_seg_hi, nseg, synT, cap, kReconcile && it == 0, bad, pp);
+                else
+                    stream_check_pass<Rule, VEC>(msg, code, s_seg_w, s_seg_lo, s_seg_hi, nseg, synT, cap, kReconcile && it == 0, (uint32_t)ahead, bad);
                 uint32_t nib = 0;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
@@ -372,12 +393,15 @@ namespace qlb
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
                     act_word[j] = __ballot_sync(0xffffffffu, (active >> j) & 1u);
+                if constexpr (kTma)
+                    tma_bit_pass<kReconcile, kBW, VEC>(msg, args, bobT, zT, lp, act_word, f0, unit, cap, clamp_b2c, pp);
+                else
                 for (int i = warp; i < n; i += kWarps)
                 {
-                    if (i + kPrefetchAhead * kWarps < n)
+                    if (i + ahead < n)
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
-                            prefetch_l2(msg + ((size_t)code.bit_slots32[(size_t)a * n + i + kPrefetchAhead * kWarps] * G + VEC * lane));
+                            prefetch_l2(msg + ((size_t)code.bit_slots32[(size_t)a * n + i + ahead] * G + VEC * lane));
                     float *row[kBW];
                     float c[kBW][VEC];
 #pragma unroll
