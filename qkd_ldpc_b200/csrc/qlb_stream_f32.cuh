@@ -25,12 +25,20 @@ namespace qlb
     {
         static __device__ __forceinline__ void load(const float *p, float (&v)[4])
         {
+#ifdef QLB_STREAM_CS
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
+#else
             const float4 t = *reinterpret_cast<const float4 *>(p);
+#endif
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         }
         static __device__ __forceinline__ void store(float *p, const float (&v)[4])
         {
+#ifdef QLB_STREAM_CS
+            __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+#else
             *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+#endif
         }
     };
     template <>
