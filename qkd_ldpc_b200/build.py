@@ -46,15 +46,34 @@ def _run(cmd, log_name):
         raise RuntimeError(f"build failed: {' '.join(str(c) for c in cmd)}")
 
 
+TRANSLATION_UNITS = ["qlb_api.cu", "qlb_tu_resident_f32.cu", "qlb_tu_stream_f32.cu", "qlb_tu_resident_f64.cu"]
+
+
 def build_library(force: bool = False, verbose_ptxas: bool = True) -> Path:
+    """One object per kernel family, compiled in parallel, linked into libqkdldpc_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     LIB_DIR.mkdir(exist_ok=True)
-    sources = [CSRC / "qlb_api.cu", CSRC / "qlb_kernels.cuh", CSRC / "qlb_layout.hpp", ROOT / "include" / "qkd_ldpc_b200.h"]
-    if not force and _newer(LIB_PATH, sources):
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + [ROOT / "include" / "qkd_ldpc_b200.h"]
+    sources = [CSRC / tu for tu in TRANSLATION_UNITS]
+    if not force and _newer(LIB_PATH, sources + headers):
         return LIB_PATH
-    cmd = [NVCC, *NVCC_FLAGS, "-shared", "-o", LIB_PATH, CSRC / "qlb_api.cu"]
-    if verbose_ptxas:
-        cmd += ["-Xptxas", "-v"]
-    _run(cmd, "build_lib.log")
+
+    def compile_tu(src: Path) -> Path:
+        obj = obj_dir / (src.stem + ".o")
+        if force or not _newer(obj, [src] + headers):
+            cmd = [NVCC, *NVCC_FLAGS, "-c", "-o", obj, src]
+            if verbose_ptxas:
+                cmd += ["-Xptxas", "-v"]
+            _run(cmd, f"build_{src.stem}.log")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(sources)) as pool:
+        objs = list(pool.map(compile_tu, sources))
+    _run([NVCC, *NVCC_FLAGS, "-shared", "-o", LIB_PATH, *objs, "-ldl"], "build_link.log")
+    (LIB_DIR / "build_lib.log").write_text("".join((LIB_DIR / f"build_{src.stem}.log").read_text() for src in sources
+                                                   if (LIB_DIR / f"build_{src.stem}.log").exists()))
     return LIB_PATH
 
 

@@ -1,11 +1,8 @@
 // C-ABI of libqkdldpc_b200.so (declared in include/qkd_ldpc_b200.h): code handles, per-GPU contexts, and the batch
 // entry points that replace the reference's per-frame hot-path functions. No CPU compute path exists here: every
 // entry that does work launches the sm_100a kernels in qlb_kernels.cuh or fails.
-#include "../../include/qkd_ldpc_b200.h"
-#include "qlb_kernels.cuh"
-#include "qlb_resident_f32.cuh"
+#include "qlb_internal.hpp"
 #include "qlb_generate.cuh"
-#include "qlb_stream_f32.cuh"
 #include "qlb_layout.hpp"
 
 #include <atomic>
@@ -24,6 +21,10 @@ using namespace qlb;
 namespace
 {
     thread_local std::string g_error;
+    std::atomic<uint64_t> g_next_code_id{1};
+}
+namespace qlb
+{
     int fail(int code, const std::string &msg)
     {
         g_error = msg;
@@ -33,72 +34,12 @@ namespace
     {
         return fail(QLB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     }
-#define QLB_CUDA(call)                                   \
-    do                                                   \
-    {                                                    \
-        cudaError_t e__ = (call);                        \
-        if (e__ != cudaSuccess)                          \
-            return cuda_fail(e__, #call);                \
-    } while (0)
-
-    std::atomic<uint64_t> g_next_code_id{1};
 }
 
 struct qlb_code
 {
     uint64_t id;
     CodeLayout L;
-};
-
-namespace
-{
-    struct DeviceCode
-    {
-        CodeDev dev{};
-        std::vector<void *> allocs;
-    };
-
-    // grow-only device buffer
-    struct DevBuf
-    {
-        void *p = nullptr;
-        size_t cap = 0;
-        cudaError_t reserve(size_t bytes)
-        {
-            if (bytes <= cap)
-                return cudaSuccess;
-            if (p)
-                cudaFree(p);
-            p = nullptr;
-            cap = 0;
-            cudaError_t e = cudaMalloc(&p, bytes);
-            if (e == cudaSuccess)
-                cap = bytes;
-            return e;
-        }
-        void release()
-        {
-            if (p)
-                cudaFree(p);
-            p = nullptr;
-            cap = 0;
-        }
-    };
-}
-
-struct qlb_ctx
-{
-    int device = 0;
-    int sm_count = 0;
-    int smem_optin = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-    unsigned long long *d_counters = nullptr; // [0] frame queue, [1] executed iterations
-    uint64_t launches = 0;
-    std::map<uint64_t, DeviceCode> codes;
-    DevBuf scratch, in_a, in_b, in_q, in_llr, in_syn, out_it, out_res, out_dec, out_syn, gen_perm, gen_seeds;
-    std::vector<double> host_logp;
-    std::vector<uint32_t> host_pack_a, host_pack_b, host_pack_out;
 };
 
 namespace
@@ -155,6 +96,15 @@ namespace
         if ((rc = upload(L.bit_slots.data(), L.bit_slots.size() * 4, dc, &p)))
             return rc;
         d.bit_slots32 = static_cast<const uint32_t *>(p);
+        if (L.n < 65536)
+        {
+            std::vector<uint16_t> c16(L.col_of_slot.size());
+            for (size_t i = 0; i < c16.size(); ++i)
+                c16[i] = L.col_of_slot[i] == kNoSlot ? 0xFFFFu : static_cast<uint16_t>(L.col_of_slot[i]);
+            if ((rc = upload(c16.data(), c16.size() * 2, dc, &p)))
+                return rc;
+            d.col_of_slot16 = static_cast<const uint16_t *>(p);
+        }
         if ((rc = upload(L.check_order.data(), L.check_order.size() * 4, dc, &p)))
             return rc;
         d.check_order = static_cast<const uint32_t *>(p);
@@ -228,107 +178,6 @@ namespace
         return launch_one<Math, kTier, kReconcile, 0, kThreads>(ctx, args);
     }
 
-    // The specialised fp32 kernel (qlb_resident_f32.cuh): whole frame in shared memory, uniform bit weight.
-    template <typename Rule, bool kReconcile, int kBW>
-    int launch_resident(qlb_ctx *ctx, DecodeArgs &args)
-    {
-        constexpr int kThreads = kResidentThreads;
-        auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kThreads>;
-        const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.slots, kBW);
-        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        long long grid = ctx->sm_count; // one resident CTA per SM
-        if (grid > args.n_frames)
-            grid = args.n_frames;
-        QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
-        args.queue = ctx->d_counters;
-        args.iter_total = ctx->d_counters + 1;
-        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(args);
-        QLB_CUDA(cudaGetLastError());
-        ++ctx->launches;
-        return QLB_OK;
-    }
-
-    template <typename Rule, bool kReconcile>
-    int launch_resident_bw(qlb_ctx *ctx, DecodeArgs &args)
-    {
-        switch (args.code.uniform_bit_w)
-        {
-        case 2: return launch_resident<Rule, kReconcile, 2>(ctx, args);
-        case 3: return launch_resident<Rule, kReconcile, 3>(ctx, args);
-        case 4: return launch_resident<Rule, kReconcile, 4>(ctx, args);
-        default: return fail(QLB_ERR_UNSUPPORTED, "resident kernel: unsupported bit weight");
-        }
-    }
-
-    bool resident_eligible(const qlb_ctx *ctx, const CodeDev &c)
-    {
-        return c.slots < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
-               c.n <= 32 * kResidentThreads && c.m <= 32 * kResidentThreads && c.n % 32 == 0 &&
-               resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) + kResidentStaticSmem <= (size_t)ctx->smem_optin;
-    }
-
-    // The frame-interleaved streaming kernel (qlb_stream_f32.cuh): messages in HBM, any block length.
-    template <typename Rule, bool kReconcile, int kBW, int VEC, bool kTma>
-    int launch_stream(qlb_ctx *ctx, DecodeArgs &args, int stages)
-    {
-        auto kern = decode_stream_f32_kernel<Rule, kReconcile, kBW, VEC, kTma>;
-        const size_t ring = kTma ? (size_t)(kStreamThreads / 32) * stages * ((size_t)std::max(args.code.max_check_w, kBW) * 128 * VEC + 8) + 128 : 0;
-        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
-        const StreamCarve cv = stream_carve(args.code.n, args.code.m, args.code.slots, VEC);
-        const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
-        long long grid = ctx->sm_count; // one resident CTA per SM
-        if (grid > groups)
-            grid = groups;
-        QLB_CUDA(ctx->scratch.reserve((size_t)grid * cv.total));
-        if (args.syndrome_out)
-            QLB_CUDA(cudaMemsetAsync(args.syndrome_out, 0, (size_t)args.n_frames * args.code.words_m * 4, ctx->stream));
-        if (std::getenv("QLB_DEBUG"))
-            std::fprintf(stderr, "[qlb] decode_stream_f32_kernel VEC=%d tma=%d stages=%d ring=%zu B: %lld groups of %lld frames, grid=%lld, %zu B scratch per group\n",
-                         VEC, (int)kTma, stages, ring, groups, G, grid, cv.total);
-        QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
-        args.queue = ctx->d_counters;
-        args.iter_total = ctx->d_counters + 1;
-        const char *pf = std::getenv("QLB_STREAM_PREFETCH"); // nodes ahead (per warp) whose rows are prefetched into L2
-        kern<<<(unsigned)grid, kStreamThreads, ring, ctx->stream>>>(args, static_cast<unsigned char *>(ctx->scratch.p), cv.total, groups,
-                                                                    pf ? std::atoi(pf) : 4, stages);
-        QLB_CUDA(cudaGetLastError());
-        ++ctx->launches;
-        return QLB_OK;
-    }
-
-    template <typename Rule, bool kReconcile>
-    int launch_stream_bw(qlb_ctx *ctx, DecodeArgs &args)
-    {
-        // 128-bit accesses (128 frames per group) unless the per-SM message arrays would not fit in device memory
-        size_t free_b = 0, total_b = 0;
-        QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need4 = (size_t)ctx->sm_count * stream_carve(args.code.n, args.code.m, args.code.slots, 4).total;
-        const bool vec4 = need4 <= (free_b + ctx->scratch.cap) / 10 * 7 && args.n_frames > 32;
-        // TMA rings: 16 warps x S stages x (rows x row bytes) of shared memory; needs S >= 3 and check weights <= 8
-        const size_t stage_bytes = (size_t)std::max(args.code.max_check_w, args.code.uniform_bit_w) * 128 * (vec4 ? 4 : 1) + 8;
-        int stages = (int)std::min<size_t>(8, ((size_t)ctx->smem_optin - 4096) / ((kStreamThreads / 32) * stage_bytes));
-        // Measured on B200 (N = 100 000, 18 944 frames): per-warp TMA rings of 512-byte bulk copies reach 0.49 of the HBM copy
-        // bandwidth, plain 128-bit loads + L2 software prefetch 0.57-0.58 -- the rings are kept as an opt-in experiment.
-        const bool tma = stages >= 3 && args.code.max_check_w <= 8 && args.code.uniform_bit_w == 3 && std::getenv("QLB_STREAM_TMA");
-        if (tma)
-            return vec4 ? launch_stream<Rule, kReconcile, 3, 4, true>(ctx, args, stages) : launch_stream<Rule, kReconcile, 3, 1, true>(ctx, args, stages);
-        switch (args.code.uniform_bit_w * 10 + (vec4 ? 4 : 1))
-        {
-        case 24: return launch_stream<Rule, kReconcile, 2, 4, false>(ctx, args, 0);
-        case 34: return launch_stream<Rule, kReconcile, 3, 4, false>(ctx, args, 0);
-        case 44: return launch_stream<Rule, kReconcile, 4, 4, false>(ctx, args, 0);
-        case 21: return launch_stream<Rule, kReconcile, 2, 1, false>(ctx, args, 0);
-        case 31: return launch_stream<Rule, kReconcile, 3, 1, false>(ctx, args, 0);
-        case 41: return launch_stream<Rule, kReconcile, 4, 1, false>(ctx, args, 0);
-        default: return fail(QLB_ERR_UNSUPPORTED, "streaming kernel: unsupported bit weight");
-        }
-    }
-
-    bool stream_eligible(const CodeDev &c)
-    {
-        return c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW && c.m <= c.n;
-    }
-
     template <typename Math, bool kReconcile>
     int launch_tier(qlb_ctx *ctx, DecodeArgs &args, int forced_tier)
     {
@@ -362,24 +211,19 @@ namespace
         args.thr = p->threshold;
         args.cap_f32 = p->enable_threshold ? (float)p->threshold : INFINITY;
         const int forced = (p->flags >> 8) & 0xF ? ((p->flags >> 8) & 0xF) - 1 : -1; // bits 8..11: test hook, tier+1
-        if (p->precision == QLB_PRECISION_F32 && forced < 0 && resident_eligible(ctx, args.code))
-        {
-            if (p->flags & QLB_FLAG_F32_FAST_MATH)
-                return launch_resident_bw<RuleF32Fast, kReconcile>(ctx, args);
-            return launch_resident_bw<RuleF32Accurate, kReconcile>(ctx, args);
-        }
+        const bool fast = (p->flags & QLB_FLAG_F32_FAST_MATH) != 0;
+        if (p->precision == QLB_PRECISION_F32 && forced < 0 && resident_f32_eligible(ctx, args.code))
+            return launch_resident_f32(ctx, args, kReconcile, fast);
         // codes too large for one SM's shared memory: frame-interleaved streaming through HBM (test hook: tier 3 forces it)
-        if (p->precision == QLB_PRECISION_F32 && (forced < 0 || forced == 3) && stream_eligible(args.code))
-        {
-            if (p->flags & QLB_FLAG_F32_FAST_MATH)
-                return launch_stream_bw<RuleF32Fast, kReconcile>(ctx, args);
-            return launch_stream_bw<RuleF32Accurate, kReconcile>(ctx, args);
-        }
+        if (p->precision == QLB_PRECISION_F32 && (forced < 0 || forced == 3) && stream_f32_eligible(args.code))
+            return launch_stream_f32(ctx, args, kReconcile, fast);
         if (forced == 3)
             return fail(QLB_ERR_UNSUPPORTED, "the streaming kernel does not handle this code / precision");
+        if (p->precision == QLB_PRECISION_F64 && forced < 0 && resident_f64_eligible(ctx, args.code))
+            return launch_resident_f64(ctx, args, kReconcile);
         if (p->precision == QLB_PRECISION_F64)
             return launch_tier<MathF64, kReconcile>(ctx, args, forced);
-        if (p->flags & QLB_FLAG_F32_FAST_MATH)
+        if (fast)
             return launch_tier<MathF32Fast, kReconcile>(ctx, args, forced);
         return launch_tier<MathF32, kReconcile>(ctx, args, forced);
     }
@@ -398,9 +242,9 @@ namespace
             while ((size_t)group * per_frame > budget)
                 group >>= 1;
         const size_t smem = stage ? (size_t)group * per_frame : 0;
-        QLB_CUDA(cudaFuncSetAttribute(syndrome_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        QLB_CUDA(cudaFuncSetAttribute(syndrome_kernel<kSynThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         const long long grid = (n_frames + group - 1) / group;
-        syndrome_kernel<<<(unsigned)grid, kSynThreads, smem, ctx->stream>>>(dev, n_frames, group, stage, d_bits, d_out);
+        syndrome_kernel<kSynThreads><<<(unsigned)grid, kSynThreads, smem, ctx->stream>>>(dev, n_frames, group, stage, d_bits, d_out);
         QLB_CUDA(cudaGetLastError());
         return QLB_OK;
     }

@@ -1,0 +1,91 @@
+// Internal declarations shared by the translation units of libqkdldpc_b200.so (not part of the C-ABI).
+// The library is split into one TU per kernel family so that they compile in parallel:
+//   qlb_api.cu            C-ABI, code/context management, generic decode_kernel, syndrome, key generator
+//   qlb_tu_resident_f32.cu / qlb_tu_stream_f32.cu / qlb_tu_resident_f64.cu   the specialised decoders + their launchers
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qkd_ldpc_b200.h"
+#include "qlb_kernels.cuh"
+
+namespace qlb
+{
+    int fail(int code, const std::string &msg);
+    int cuda_fail(cudaError_t e, const char *what);
+}
+#define QLB_CUDA(call)                                   \
+    do                                                   \
+    {                                                    \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess)                          \
+            return qlb::cuda_fail(e__, #call);           \
+    } while (0)
+
+namespace qlb
+{
+    struct DeviceCode
+    {
+        CodeDev dev{};
+        std::vector<void *> allocs;
+    };
+
+    // grow-only device buffer
+    struct DevBuf
+    {
+        void *p = nullptr;
+        size_t cap = 0;
+        cudaError_t reserve(size_t bytes)
+        {
+            if (bytes <= cap)
+                return cudaSuccess;
+            if (p)
+                cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e == cudaSuccess)
+                cap = bytes;
+            return e;
+        }
+        void release()
+        {
+            if (p)
+                cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+    };
+}
+
+struct qlb_ctx
+{
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    unsigned long long *d_counters = nullptr; // [0] frame queue, [1] executed iterations
+    uint64_t launches = 0;
+    std::map<uint64_t, qlb::DeviceCode> codes;
+    qlb::DevBuf scratch, in_a, in_b, in_q, in_llr, in_syn, out_it, out_res, out_dec, out_syn, gen_perm, gen_seeds;
+    std::vector<double> host_logp;
+    std::vector<uint32_t> host_pack_a, host_pack_b, host_pack_out;
+};
+
+namespace qlb
+{
+    // launchers of the specialised decoders (each in its own TU); `fast`: the SFU check rule
+    bool resident_f32_eligible(const qlb_ctx *ctx, const CodeDev &c);
+    int launch_resident_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);
+    bool stream_f32_eligible(const CodeDev &c);
+    int launch_stream_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);
+    bool resident_f64_eligible(const qlb_ctx *ctx, const CodeDev &c);
+    int launch_resident_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile);
+}

@@ -43,6 +43,7 @@ namespace qlb
         uint32_t base4[16];    // 4 * base[k] for the fp32 resident kernel (byte offsets, constant-bank operands)
         const uint16_t *bit_slots16; // [max_bit_w][n] (0xFFFF = none), valid when e < 65535
         const uint32_t *bit_slots32; // [max_bit_w][n] (0xFFFFFFFF = none)
+        const uint16_t *col_of_slot16; // [slots] bit index of the edge stored at a slot, valid when n < 65536
         const uint32_t *check_order; // [m]
         const int32_t *row_ptr;      // [m+1]
         const int32_t *col_idx;      // [e]
@@ -610,7 +611,8 @@ namespace qlb
     // calculate_syndrome_irregular (src/array_and_matrix_operations.cpp:476-486).
     constexpr int kSynFrames = 8;
     constexpr int kSynThreads = 256;
-    __global__ void __launch_bounds__(kSynThreads) syndrome_kernel(const CodeDev code, long long n_frames, int group, int stage,
+    template <int kThreads> // (a template so that the header can be included by several translation units)
+    __global__ void __launch_bounds__(kThreads) syndrome_kernel(const CodeDev code, long long n_frames, int group, int stage,
                                                                   const uint32_t *bits, uint32_t *syndrome_out)
     {
         extern __shared__ __align__(16) unsigned char smem[];

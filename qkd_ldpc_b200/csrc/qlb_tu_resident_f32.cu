@@ -1,0 +1,56 @@
+#include "qlb_internal.hpp"
+#include <algorithm>
+using namespace qlb;
+#include "qlb_resident_f32.cuh"
+
+namespace
+{
+    // The specialised fp32 kernel (qlb_resident_f32.cuh): whole frame in shared memory, uniform bit weight.
+    template <typename Rule, bool kReconcile, int kBW>
+    int launch_resident(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        constexpr int kThreads = kResidentThreads;
+        auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kThreads>;
+        const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.slots, kBW);
+        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long grid = ctx->sm_count; // one resident CTA per SM
+        if (grid > args.n_frames)
+            grid = args.n_frames;
+        QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+        args.queue = ctx->d_counters;
+        args.iter_total = ctx->d_counters + 1;
+        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(args);
+        QLB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+        return QLB_OK;
+    }
+
+    template <typename Rule, bool kReconcile>
+    int launch_resident_bw(qlb_ctx *ctx, DecodeArgs &args)
+    {
+        switch (args.code.uniform_bit_w)
+        {
+        case 2: return launch_resident<Rule, kReconcile, 2>(ctx, args);
+        case 3: return launch_resident<Rule, kReconcile, 3>(ctx, args);
+        case 4: return launch_resident<Rule, kReconcile, 4>(ctx, args);
+        default: return fail(QLB_ERR_UNSUPPORTED, "resident kernel: unsupported bit weight");
+        }
+    }
+
+}
+namespace qlb
+{
+    bool resident_f32_eligible(const qlb_ctx *ctx, const CodeDev &c)
+    {
+        return c.slots < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
+               c.n <= 32 * kResidentThreads && c.m <= 32 * kResidentThreads && c.n % 32 == 0 &&
+               resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) + kResidentStaticSmem <= (size_t)ctx->smem_optin;
+    }
+
+    int launch_resident_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast)
+    {
+        if (fast)
+            return reconcile ? launch_resident_bw<RuleF32Fast, true>(ctx, args) : launch_resident_bw<RuleF32Fast, false>(ctx, args);
+        return reconcile ? launch_resident_bw<RuleF32Accurate, true>(ctx, args) : launch_resident_bw<RuleF32Accurate, false>(ctx, args);
+    }
+}
