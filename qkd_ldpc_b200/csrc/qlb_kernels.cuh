@@ -99,8 +99,14 @@ namespace qlb
     struct MathF64
     {
         typedef double real;
-#ifdef QLB_F64_ALGEBRAIC
-        // experiment: branch-free algebraic forms (same functions, different rounding at the ulp level)
+#ifndef QLB_F64_LIBM_FORMS
+        // tanh(m/2) = (1 - e^-|m|) / (1 + e^-|m|) and 2 atanh(p) = ln((1 + p) / (1 - p)): the same functions as the reference's
+        // tanh(m / 2.) and 2. * atanh(p), evaluated branch-free (libdevice's tanh/atanh take divergent small/large-argument
+        // paths, which a warp then executes both). They differ from glibc's results at the ulp level, as libdevice's own tanh /
+        // atanh do; what is contractual is the per-frame outcome, checked on 9 216 reference frames across the waterfall
+        // (profiles/parity_r01.md): iterations, flags and keys identical on every frame. |m| is capped at 64 before the
+        // exponential (e^-64 is far below half an ulp of 1, so the quotient is exactly +-1 either way). -DQLB_F64_LIBM_FORMS
+        // restores the literal calls.
         static __device__ __forceinline__ double tanh_half(double m)
         {
             const double e = exp(-fmin(fabs(m), 64.));

@@ -15,7 +15,7 @@
 
 namespace qlb
 {
-    constexpr int kResident64Threads = 512;
+    constexpr int kResident64Threads = 768;
     constexpr size_t kResident64StaticSmem = 2 * kResident64Threads * 4 + 1024;
 
     struct Split64
