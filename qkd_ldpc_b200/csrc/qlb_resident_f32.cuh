@@ -204,6 +204,7 @@ namespace qlb
     }
 
     constexpr int kResidentMaxCW = 16;
+    constexpr int kBitUnroll = 1; // bits per thread in flight in the bit pass (2 measured no faster: the pass is bandwidth-, not latency-bound)
     constexpr int kResidentThreads = 1024;
     constexpr size_t kResidentStaticSmem = 2 * kResidentThreads * 4 + 512; // static bookkeeping declared inside the kernel
 
@@ -223,7 +224,7 @@ namespace qlb
         const uint16_t *bs = bslot + tid;
         uint32_t *zw = s_z + (tid >> 5);
         const bool lane0 = (tid & 31) == 0;
-#pragma unroll 1
+#pragma unroll kBitUnroll
         for (int i = tid; i < n; i += kThreads)
         {
             float prior;
