@@ -171,10 +171,13 @@ namespace
     int launch_shape(qlb_ctx *ctx, DecodeArgs &args)
     {
         const int cw = args.code.max_check_w, bw = args.code.max_bit_w;
-        if (kTier != kTierGlobal && bw <= 4 && cw <= 8)
-            return launch_one<Math, kTier, kReconcile, 8, kThreads>(ctx, args);
-        if (kTier != kTierGlobal && bw <= 4 && cw <= 16)
-            return launch_one<Math, kTier, kReconcile, 16, kThreads>(ctx, args);
+        if constexpr (kTier != kTierGlobal) // register-tile variants exist for the shared-memory tiers only
+        {
+            if (bw <= 4 && cw <= 8)
+                return launch_one<Math, kTier, kReconcile, 8, kThreads>(ctx, args);
+            if (bw <= 4 && cw <= 16)
+                return launch_one<Math, kTier, kReconcile, 16, kThreads>(ctx, args);
+        }
         return launch_one<Math, kTier, kReconcile, 0, kThreads>(ctx, args);
     }
 
@@ -193,7 +196,7 @@ namespace
             tier = kTierSmemAll;
         if (forced_tier >= 0 && forced_tier >= tier)
             tier = forced_tier; // tests may force a slower tier, never one that does not fit
-        if (sizeof(Real) == 4)
+        if constexpr (sizeof(Real) == 4) // fp64 messages never fit a whole frame in shared memory
         {
             if (tier == kTierSmemAll)
                 return launch_shape<Math, kTierSmemAll, kReconcile, 1024>(ctx, args);

@@ -7,14 +7,14 @@ namespace
 {
     // The frame-interleaved streaming kernel (qlb_stream_f32.cuh): messages in HBM, any block length.
     template <typename Rule, bool kReconcile, int kBW, int VEC, bool kTma>
-    int launch_stream(qlb_ctx *ctx, DecodeArgs &args, int stages)
+    int launch_stream(qlb_ctx *ctx, DecodeArgs &args, int stages, long long max_ctas)
     {
         auto kern = decode_stream_f32_kernel<Rule, kReconcile, kBW, VEC, kTma>;
         const size_t ring = kTma ? (size_t)(kStreamThreads / 32) * stages * ((size_t)std::max(args.code.max_check_w, kBW) * 128 * VEC + 8) + 128 : 0;
         QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
         const StreamCarve cv = stream_carve(args.code.n, args.code.m, args.code.slots, VEC);
         const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
-        long long grid = ctx->sm_count; // one resident CTA per SM
+        long long grid = std::min<long long>(ctx->sm_count, max_ctas); // one resident CTA per SM, fewer when HBM cannot hold more groups
         if (grid > groups)
             grid = groups;
         QLB_CUDA(ctx->scratch.reserve((size_t)grid * cv.total));
@@ -40,8 +40,14 @@ namespace
         // 128-bit accesses (128 frames per group) unless the per-SM message arrays would not fit in device memory
         size_t free_b = 0, total_b = 0;
         QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need4 = (size_t)ctx->sm_count * stream_carve(args.code.n, args.code.m, args.code.slots, 4).total;
-        const bool vec4 = need4 <= (free_b + ctx->scratch.cap) / 10 * 7 && args.n_frames > 32;
+        // 128 frames per group (128-bit accesses, 512-byte rows) as long as device memory holds the message arrays of enough
+        // groups to keep at least 40 % of the SMs busy; else 32 frames per group (measured at N = 1 000 000: 0.23 of the HBM
+        // copy bandwidth with 32-frame groups on all SMs)
+        const size_t per_group4 = stream_carve(args.code.n, args.code.m, args.code.slots, 4).total;
+        const size_t budget = (free_b + ctx->scratch.cap) / 20 * 17;
+        const long long fit4 = (long long)(budget / per_group4), fit1 = (long long)(budget / stream_carve(args.code.n, args.code.m, args.code.slots, 1).total);
+        const bool vec4 = args.n_frames > 32 && fit4 * 5 >= (long long)ctx->sm_count * 2;
+        const long long max_ctas = std::max<long long>(1, vec4 ? fit4 : fit1);
         // TMA rings: 16 warps x S stages x (rows x row bytes) of shared memory; needs S >= 3 and check weights <= 8
         const size_t stage_bytes = (size_t)std::max(args.code.max_check_w, args.code.uniform_bit_w) * 128 * (vec4 ? 4 : 1) + 8;
         int stages = (int)std::min<size_t>(8, ((size_t)ctx->smem_optin - 4096) / ((kStreamThreads / 32) * stage_bytes));
@@ -49,11 +55,12 @@ namespace
         // bandwidth, plain 128-bit loads + L2 software prefetch 0.57-0.58 -- the rings are kept as an opt-in experiment.
         const bool tma = stages >= 3 && args.code.max_check_w <= 8 && args.code.uniform_bit_w == 3 && std::getenv("QLB_STREAM_TMA");
         if (tma)
-            return vec4 ? launch_stream<Rule, kReconcile, 3, 4, true>(ctx, args, stages) : launch_stream<Rule, kReconcile, 3, 1, true>(ctx, args, stages);
+            return vec4 ? launch_stream<Rule, kReconcile, 3, 4, true>(ctx, args, stages, max_ctas)
+                        : launch_stream<Rule, kReconcile, 3, 1, true>(ctx, args, stages, max_ctas);
         switch (args.code.uniform_bit_w * 10 + (vec4 ? 4 : 1))
         {
-        case 34: return launch_stream<Rule, kReconcile, 3, 4, false>(ctx, args, 0);
-        case 31: return launch_stream<Rule, kReconcile, 3, 1, false>(ctx, args, 0);
+        case 34: return launch_stream<Rule, kReconcile, 3, 4, false>(ctx, args, 0, max_ctas);
+        case 31: return launch_stream<Rule, kReconcile, 3, 1, false>(ctx, args, 0, max_ctas);
         default: return fail(QLB_ERR_UNSUPPORTED, "streaming kernel: unsupported bit weight");
         }
     }

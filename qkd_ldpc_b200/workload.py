@@ -43,9 +43,12 @@ def make_frames(n: int, words: int, n_frames: int, q: float, seed: int, device, 
     for lo in range(0, n_frames, chunk):
         f = min(chunk, n_frames - lo)
         alice = torch.randint(0, 2, (f, n), dtype=torch.uint8, device=device, generator=gen)
-        pos = torch.rand((f, n), device=device, generator=gen).topk(n_err, dim=1).indices
-        flip = torch.zeros((f, n), dtype=torch.uint8, device=device)
-        flip.scatter_(1, pos, 1)
+        if n <= 65536:
+            pos = torch.rand((f, n), device=device, generator=gen).topk(n_err, dim=1).indices
+            flip = torch.zeros((f, n), dtype=torch.uint8, device=device)
+            flip.scatter_(1, pos, 1)
+        else:  # very long keys (throughput probes only): i.i.d. flips with probability q instead of an exact count
+            flip = (torch.rand((f, n), device=device, generator=gen) < (n_err / n)).to(torch.uint8)
         a_out[lo:lo + f] = _pack(alice, words)
         b_out[lo:lo + f] = _pack(alice ^ flip, words)
     return a_out, b_out, n_err / n

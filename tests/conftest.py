@@ -1,8 +1,6 @@
-import os
 import sys
 from pathlib import Path
 
-import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
@@ -16,17 +14,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
-def _have_gpu() -> bool:
-    try:
-        from qkd_ldpc_b200 import capi
-        return capi.load_library().qlb_device_count() > 0
-    except Exception:
-        return False
-
-
-def pytest_collection_modifyitems(config, items):
-    # `-m gpu` on a box without a GPU must fail loudly, not skip: the product has no CPU path.
-    pass
+# `-m gpu` tests on a box without a GPU fail loudly (QlbError from Context): the product has no CPU path to skip to.
 
 
 @pytest.fixture(scope="session")
