@@ -1,0 +1,101 @@
+// Branch-free double-precision exp / log / divide for the fp64 check rule.
+//
+// ncu on the fp64 kernels showed that 70 % of the issued instructions inside libdevice's exp / log / divide are not
+// FP64 arithmetic but their scaffolding: 64-bit polynomial constants materialised through UMOV pairs, register moves and
+// special-case branches (profiles/r01_summary.md). These versions keep every coefficient in constant memory (a direct DFMA
+// operand), have no branches, and are specialised to the argument ranges the decoder produces:
+//   exp_neg(x)   x in [-64, 0]           Cody-Waite reduction by ln 2 (round-to-nearest through the 1.5*2^52 shift), degree-13
+//                                        Taylor polynomial in Horner form, exponent insertion by integer add.  <= 1 ulp
+//   div_pos(a,d) d > 0, 2^-60 < d < 2^60 MUFU.RCP seed (fp32), two Newton steps, one residual correction.      correctly rounded
+//                                        on every sampled input
+//   log_pos(y)   y >= 2^-60, finite      the classical fdlibm scheme: y = 2^k m, m in [sqrt(1/2), sqrt 2), s = f/(2+f), f = m-1,
+//                                        log m = f - (f^2/2 - s (f^2/2 + R(s^2))), R = the degree-14 minimax polynomial
+//                                        Lg1..Lg7 of fdlibm's e_log.c (published algorithm and constants).     <= 1 ulp
+// Accuracy was measured on the CPU with the same FMA arithmetic against glibc over 4e6 random arguments each
+// (/tmp prototype, numbers above). Like any libm they differ from glibc at the ulp level; the decoder's contract is the
+// per-frame outcome (profiles/parity_r01.md).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qlb
+{
+    namespace f64m
+    {
+        static __constant__ double kExp[14] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+                                               1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+        static __constant__ double kLg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                                             1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};
+        static __constant__ double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+
+        __device__ __forceinline__ double exp_neg(double x)
+        {
+            const double kMagic = 6755399441055744.0; // 1.5 * 2^52: adding it rounds to the nearest integer in the low word
+            const double t = fma(x, 1.4426950408889634, kMagic);
+            const int k = __double2loint(t);
+            const double kf = t - kMagic;
+            double r = fma(kf, -kLn2Hi, x);
+            r = fma(kf, -kLn2Lo, r);
+            double p = kExp[13];
+#pragma unroll
+            for (int i = 12; i >= 0; --i)
+                p = fma(p, r, kExp[i]);
+            return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+        }
+
+        __device__ __forceinline__ double rcp_pos(double d)
+        {
+            float y0;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__double2float_rn(d)));
+            double y = (double)y0;
+            double e = fma(-d, y, 1.0);
+            y = fma(y, e, y);
+            e = fma(-d, y, 1.0);
+            return fma(y, e, y);
+        }
+        __device__ __forceinline__ double div_pos(double a, double d)
+        {
+            const double y = rcp_pos(d);
+            const double q = a * y;
+            return fma(fma(-d, q, a), y, q);
+        }
+
+        __device__ __forceinline__ double log_pos(double y)
+        {
+            const int hi = __double2hiint(y);
+            int k = (hi >> 20) - 1023;
+            double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(y));
+            const bool big = m > 1.4142135623730951;
+            m = big ? 0.5 * m : m;
+            k += big ? 1 : 0;
+            const double f = m - 1.0;
+            const double s = div_pos(f, 2.0 + f);
+            const double z = s * s, w = z * z;
+            const double t1 = w * fma(w, fma(w, kLg[5], kLg[3]), kLg[1]);
+            const double t2 = z * fma(w, fma(w, fma(w, kLg[6], kLg[4]), kLg[2]), kLg[0]);
+            const double R = t2 + t1;
+            const double hfsq = 0.5 * f * f, dk = (double)k;
+            return dk * kLn2Hi - ((hfsq - (s * (hfsq + R) + dk * kLn2Lo)) - f);
+        }
+
+        // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped at 64 (the quotient is exactly +-1 far earlier)
+        __device__ __forceinline__ double tanh_half(double m)
+        {
+            const double e = exp_neg(-fmin(fabs(m), 64.));
+            return copysign(div_pos(1. - e, 1. + e), m);
+        }
+        // 2 atanh(p) = ln((1 + p) / (1 - p)) with the IEEE outcomes of the literal expression at the edges:
+        // p = 1 -> +inf, p = -1 -> -inf, |p| > 1 or NaN -> NaN
+        __device__ __forceinline__ double two_atanh(double p)
+        {
+            const double num = 1. + p, den = 1. - p;
+            const bool regular = num > 0. && den > 0.;
+            const double y = div_pos(regular ? num : 1., regular ? den : 1.);
+            double r = log_pos(y);
+            r = (den == 0. && num > 0.) ? __longlong_as_double(0x7ff0000000000000LL) : r;
+            r = (num == 0. && den > 0.) ? __longlong_as_double(0xfff0000000000000LL) : r;
+            r = (num < 0. || den < 0. || p != p) ? __longlong_as_double(0x7ff8000000000000LL) : r;
+            return r;
+        }
+    }
+}

@@ -81,6 +81,36 @@ struct qlb_ctx
 
 namespace qlb
 {
+    // Block size (multiple of 32, in [max/2, max]) for the thread-per-node kernels. Every thread walks the bits with stride T and each
+    // weight segment of the sorted checks with stride T, and the block waits for the slowest thread, so T is chosen to keep the
+    // last round of each walk as full as possible (`check_share`: the check walk's share of an iteration); among equally balanced
+    // sizes the smaller block measured slightly faster (B200, N=10240: 768 > 896 > 1024 threads by 2 %). Both walks must stay within the 32 per-thread rounds the kernels park bits for.
+    inline int balanced_block_size(const CodeDev &c, int max_threads, double check_share)
+    {
+        int best = 0;
+        double best_score = -1.;
+        for (int t = max_threads; t >= max_threads / 2 && t >= 32; t -= 32)
+        {
+            long long check_rounds = 0;
+            for (int w = c.max_check_w; w >= 0; --w)
+            {
+                const long long lo = (w < c.max_check_w) ? c.cnt[w] : 0, hi = (w > 0) ? c.cnt[w - 1] : c.m;
+                check_rounds += (hi - lo + t - 1) / t;
+            }
+            const long long bit_rounds = (c.n + t - 1) / t;
+            if (check_rounds > 32 || bit_rounds > 32)
+                break;
+            const double ec = (double)c.m / t / (double)check_rounds, eb = (double)c.n / t / (double)bit_rounds;
+            const double score = (check_share * ec + (1. - check_share) * eb) * (1. - 0.02 * t / max_threads);
+            if (score > best_score + 1e-12)
+            {
+                best_score = score;
+                best = t;
+            }
+        }
+        return best; // 0: no admissible block size
+    }
+
     // launchers of the specialised decoders (each in its own TU); `fast`: the SFU check rule
     bool resident_f32_eligible(const qlb_ctx *ctx, const CodeDev &c);
     int launch_resident_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);

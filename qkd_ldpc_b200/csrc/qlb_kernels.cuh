@@ -22,6 +22,8 @@
 #include <stdint.h>
 #include <type_traits>
 
+#include "qlb_f64_math.cuh"
+
 namespace qlb
 {
     constexpr int kMaxCW = 64;
@@ -99,14 +101,17 @@ namespace qlb
     struct MathF64
     {
         typedef double real;
-#ifndef QLB_F64_LIBM_FORMS
+#if !defined(QLB_F64_LIBM_FORMS) && !defined(QLB_F64_LIBDEVICE_EXPLOG)
         // tanh(m/2) = (1 - e^-|m|) / (1 + e^-|m|) and 2 atanh(p) = ln((1 + p) / (1 - p)): the same functions as the reference's
-        // tanh(m / 2.) and 2. * atanh(p), evaluated branch-free (libdevice's tanh/atanh take divergent small/large-argument
-        // paths, which a warp then executes both). They differ from glibc's results at the ulp level, as libdevice's own tanh /
-        // atanh do; what is contractual is the per-frame outcome, checked on 9 216 reference frames across the waterfall
-        // (profiles/parity_r01.md): iterations, flags and keys identical on every frame. |m| is capped at 64 before the
-        // exponential (e^-64 is far below half an ulp of 1, so the quotient is exactly +-1 either way). -DQLB_F64_LIBM_FORMS
-        // restores the literal calls.
+        // tanh(m / 2.) and 2. * atanh(p), evaluated branch-free with the constant-memory exp / log / divide of qlb_f64_math.cuh
+        // (libdevice's tanh/atanh take divergent small/large-argument paths, and 70 % of what its exp/log/divide issue is
+        // constant and register shuffling). They differ from glibc's results at the ulp level, as libdevice's own do; what is
+        // contractual is the per-frame outcome, checked on 9 216 + 10 240 reference frames (profiles/parity_r01.md,
+        // multirate_r01.md). -DQLB_F64_LIBDEVICE_EXPLOG keeps the forms but calls libdevice exp/log and operator/;
+        // -DQLB_F64_LIBM_FORMS restores the literal tanh / atanh calls.
+        static __device__ __forceinline__ double tanh_half(double m) { return f64m::tanh_half(m); }
+        static __device__ __forceinline__ double two_atanh(double p) { return f64m::two_atanh(p); }
+#elif defined(QLB_F64_LIBDEVICE_EXPLOG)
         static __device__ __forceinline__ double tanh_half(double m)
         {
             const double e = exp(-fmin(fabs(m), 64.));

@@ -167,8 +167,8 @@ namespace qlb
 
     // All checks of weight exactly W: sorted positions [lo, hi). Round r of the thread's walk uses bit `rbit` of my_syn.
     // Returns the OR over the thread's checks of (parity of the riding hard decisions) ^ (syndrome bit), in bit 0.
-    template <typename Rule, int W, int kThreads, typename Base>
-    __device__ __forceinline__ uint32_t check_segment(unsigned char *__restrict__ msg_bytes, const Base base4, uint32_t lo, uint32_t hi,
+    template <typename Rule, int W, typename Base>
+    __device__ __forceinline__ uint32_t check_segment(const int kThreads, unsigned char *__restrict__ msg_bytes, const Base base4, uint32_t lo, uint32_t hi,
                                                       uint32_t my_syn, int &rbit, float cap)
     {
         uint32_t bad = 0;
@@ -195,11 +195,11 @@ namespace qlb
     }
 
     // weights 9..16 are kept out of line: their register appetite must not leak into the hot (narrow) instantiations
-    template <typename Rule, int W, int kThreads>
-    __device__ __noinline__ uint32_t check_segment_wide(unsigned char *msg_bytes, const uint32_t *s_base4, uint32_t lo, uint32_t hi,
+    template <typename Rule, int W>
+    __device__ __noinline__ uint32_t check_segment_wide(const int kThreads, unsigned char *msg_bytes, const uint32_t *s_base4, uint32_t lo, uint32_t hi,
                                                         uint32_t my_syn, int rbit, float cap)
     {
-        const uint32_t bad = check_segment<Rule, W, kThreads>(msg_bytes, BaseFromSmem{s_base4}, lo, hi, my_syn, rbit, cap);
+        const uint32_t bad = check_segment<Rule, W>(kThreads, msg_bytes, BaseFromSmem{s_base4}, lo, hi, my_syn, rbit, cap);
         return (bad & 1u) | ((uint32_t)rbit << 1); // bit 0: parity failure, bits 1..: advanced round counter
     }
 
@@ -216,8 +216,8 @@ namespace qlb
 
     // One bit pass over the thread's bits: total (:256-258), hard decision (:259-266), extrinsic (+ clamp) (:300-316).
     // kClamp = false when the clamp cannot change what the check rule sees (see decode_resident_f32_kernel).
-    template <bool kReconcile, bool kClamp, int kBW, int kThreads>
-    __device__ __forceinline__ void bit_pass(unsigned char *__restrict__ msg_bytes, const uint16_t *__restrict__ bslot, uint32_t *__restrict__ s_z,
+    template <bool kReconcile, bool kClamp, int kBW>
+    __device__ __forceinline__ void bit_pass(const int kThreads, unsigned char *__restrict__ msg_bytes, const uint16_t *__restrict__ bslot, uint32_t *__restrict__ s_z,
                                              int n, uint32_t my_bob, float lp, const double *__restrict__ llr_f, float unit, float cap)
     {
         const int tid = threadIdx.x;
@@ -260,20 +260,21 @@ namespace qlb
             if (lane0)
                 *zw = word;
             bs += kThreads;
-            zw += kThreads / 32;
+            zw += kThreads >> 5;
         }
     }
 
     // kBW: the (uniform) bit weight. Host-checked requirements: slots < 65535, max_check_w <= 16, every bit of weight kBW,
     // n % 32 == 0, and m, n <= 32 * kThreads (one register bit per node a thread visits).
-    template <typename Rule, bool kReconcile, int kBW, int kThreads>
-    __global__ void __launch_bounds__(kThreads, 1) decode_resident_f32_kernel(const DecodeArgs args)
+    template <typename Rule, bool kReconcile, int kBW, int kMaxThreads>
+    __global__ void __launch_bounds__(kMaxThreads, 1) decode_resident_f32_kernel(const DecodeArgs args)
     {
+        const int kThreads = blockDim.x; // multiple of 32 chosen by the host (balanced_block_size), <= kMaxThreads
         extern __shared__ __align__(16) unsigned char smem[];
         // small bookkeeping at fixed (static) shared addresses
         __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
         __shared__ uint32_t s_base4[kResidentMaxCW];
-        __shared__ uint32_t s_park_bob[kThreads], s_park_syn[kThreads];
+        __shared__ uint32_t s_park_bob[kMaxThreads], s_park_syn[kMaxThreads];
         __shared__ int s_nseg;
         __shared__ __align__(8) uint64_t s_bar;
         __shared__ long long s_frame;
@@ -434,8 +435,8 @@ namespace qlb
                         const uint32_t lo = s_seg_lo[sg], hi = s_seg_hi[sg];
                         switch (s_seg_w[sg])
                         {
-#define QLB_SEG(W_) case W_: bad |= check_segment<Rule, W_, kThreads>(msg_bytes, BaseFromParams{args}, lo, hi, my_syn, rbit, cap); break;
-#define QLB_SEGW(W_) case W_: { const uint32_t rv = check_segment_wide<Rule, W_, kThreads>(msg_bytes, s_base4, lo, hi, my_syn, rbit, cap); bad |= rv & 1u; rbit = (int)(rv >> 1); } break;
+#define QLB_SEG(W_) case W_: bad |= check_segment<Rule, W_>(kThreads, msg_bytes, BaseFromParams{args}, lo, hi, my_syn, rbit, cap); break;
+#define QLB_SEGW(W_) case W_: { const uint32_t rv = check_segment_wide<Rule, W_>(kThreads, msg_bytes, s_base4, lo, hi, my_syn, rbit, cap); bad |= rv & 1u; rbit = (int)(rv >> 1); } break;
                             QLB_SEG(1) QLB_SEG(2) QLB_SEG(3) QLB_SEG(4) QLB_SEG(5) QLB_SEG(6) QLB_SEG(7) QLB_SEG(8)
                             QLB_SEGW(9) QLB_SEGW(10) QLB_SEGW(11) QLB_SEGW(12) QLB_SEGW(13) QLB_SEGW(14) QLB_SEGW(15) QLB_SEGW(16)
 #undef QLB_SEG
@@ -456,9 +457,9 @@ namespace qlb
                 if (it == args.max_it)
                     break; // :337-344
                 if (clamp_b2c)
-                    bit_pass<kReconcile, true, kBW, kThreads>(msg_bytes, bslot, s_z, n, s_park_bob[tid], lp, llr_f, unit, cap);
+                    bit_pass<kReconcile, true, kBW>(kThreads, msg_bytes, bslot, s_z, n, s_park_bob[tid], lp, llr_f, unit, cap);
                 else
-                    bit_pass<kReconcile, false, kBW, kThreads>(msg_bytes, bslot, s_z, n, s_park_bob[tid], lp, llr_f, unit, cap);
+                    bit_pass<kReconcile, false, kBW>(kThreads, msg_bytes, bslot, s_z, n, s_park_bob[tid], lp, llr_f, unit, cap);
                 ++it;
                 __syncthreads();
             }

@@ -9,8 +9,14 @@ namespace
     template <typename Rule, bool kReconcile, int kBW>
     int launch_resident(qlb_ctx *ctx, DecodeArgs &args)
     {
-        constexpr int kThreads = kResidentThreads;
-        auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kThreads>;
+        auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kResidentThreads>;
+        int kThreads = balanced_block_size(args.code, kResidentThreads, 0.55);
+        if (const char *e = std::getenv("QLB_RES32_THREADS")) // experiments only
+        {
+            const int t = std::atoi(e) / 32 * 32;
+            if (t >= 32 && t <= kResidentThreads && 32 * t >= args.code.n && 32 * t >= args.code.m)
+                kThreads = t;
+        }
         const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.slots, kBW);
         QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long grid = ctx->sm_count; // one resident CTA per SM
@@ -43,7 +49,7 @@ namespace qlb
     bool resident_f32_eligible(const qlb_ctx *ctx, const CodeDev &c)
     {
         return c.slots < 65535 && c.bit_slots16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW &&
-               c.n <= 32 * kResidentThreads && c.m <= 32 * kResidentThreads && c.n % 32 == 0 &&
+               balanced_block_size(c, kResidentThreads, 0.55) > 0 && c.n % 32 == 0 &&
                resident_smem_bytes(c.n, c.m, c.slots, c.uniform_bit_w) + kResidentStaticSmem <= (size_t)ctx->smem_optin;
     }
 

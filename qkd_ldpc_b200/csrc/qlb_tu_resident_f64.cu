@@ -15,15 +15,21 @@ namespace
     bool resident64_eligible_impl(const qlb_ctx *ctx, const CodeDev &c)
     {
         return c.slots < 65535 && c.n < 65536 && c.bit_slots16 && c.col_of_slot16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 &&
-               c.max_check_w <= 8 && c.n % 32 == 0 && c.n <= 32 * kResident64Threads && c.m <= 32 * kResident64Threads &&
+               c.max_check_w <= 8 && c.n % 32 == 0 && balanced_block_size(c, kResident64Threads, 0.85) > 0 &&
                (size_t)ctx->smem_optin > kResident64StaticSmem + resident64_small_bytes(c.n, c.m) + 8192 &&
                resident64_smem_slots(ctx, c) >= (uint32_t)c.slots / 2;
     }
     template <bool kReconcile, int kBW>
     int launch_resident64(qlb_ctx *ctx, DecodeArgs &args)
     {
-        constexpr int kThreads = kResident64Threads;
-        auto kern = decode_resident_f64_kernel<kReconcile, kBW, kThreads>;
+        auto kern = decode_resident_f64_kernel<kReconcile, kBW, kResident64Threads>;
+        int kThreads = balanced_block_size(args.code, kResident64Threads, 0.85);
+        if (const char *e = std::getenv("QLB_RES64_THREADS")) // experiments only
+        {
+            const int t = std::atoi(e) / 32 * 32;
+            if (t >= 32 && t <= kResident64Threads && 32 * t >= args.code.n && 32 * t >= args.code.m)
+                kThreads = t;
+        }
         const uint32_t smem_slots = resident64_smem_slots(ctx, args.code);
         const size_t smem = (size_t)smem_slots * 8 + resident64_small_bytes(args.code.n, args.code.m);
         QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -136,6 +136,7 @@ int main(int argc, char **argv)
         sim_inputs.clear();
         std::cout << "The results will be written to the directory: " << (root / "results").string() << "\n";
         write_file(results, root / "results");
+        qkd_b200::write_report(qkd_b200::last_sweep_report(), root / "results");
         const auto &rep = qkd_b200::last_sweep_report();
         std::cout << "frames " << rep.frames << ", frame-iterations " << rep.frame_iterations << ", " << rep.gpus << " GPU(s), " << rep.seconds_total
                   << " s total (" << rep.seconds_device << " s in device calls per GPU): " << rep.frames / rep.seconds_total << " frames/s\n";

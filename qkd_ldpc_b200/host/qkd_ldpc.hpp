@@ -142,15 +142,31 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
 // ---- implementation hooks (not in the reference) -----------------------------------------------------------------------
 namespace qkd_b200
 {
-    struct sweep_report // throughput side-report of the last QKD_LDPC_batch_simulation (never written into the CSV)
+    struct point_report // one (matrix, QBER) point of the last sweep
+    {
+        size_t sim_number{};
+        std::string matrix_filename{};
+        size_t num_bit_nodes{}, num_check_nodes{};
+        double exact_qber{};
+        size_t frames{};
+        size_t frame_iterations{}; // executed BP iterations summed over the frames
+        double seconds{};          // wall time of the point (generation + transfers + decode, all GPUs)
+    };
+    struct sweep_report // throughput side-report of the last QKD_LDPC_batch_simulation (never written into the reference CSV)
     {
         double seconds_total{};
         double seconds_device{};
         size_t frames{};
         size_t frame_iterations{};
         int gpus{};
+        std::vector<point_report> points{};
     };
     const sweep_report &last_sweep_report();
+    // Side file next to the reference-format CSV: per-point throughput, sifted-key rate, reconciliation efficiency
+    // f = (1 - R) / h2(q) and leaked bits per frame (= M: plain syndrome coding). SURVEY.md 8f-3.
+    void write_report(const sweep_report &report, fs::path directory);
+    // Non-fatal findings about a loaded matrix (unsorted adjacency lists, duplicate edges); SURVEY.md 8f-2.
+    std::vector<std::string> matrix_warnings(const H_matrix &matrix);
     // Seeded PEG construction of a column-weight-`dv` code, written as an alist file (host/peg.cpp).
     void generate_peg_alist(size_t n, size_t m, size_t dv, uint64_t seed, size_t bfs_limit, const fs::path &out_path);
     void release_device_state(); // frees cached device codes / contexts (also done at process exit)

@@ -138,6 +138,51 @@ namespace
 namespace qkd_b200
 {
     const sweep_report &last_sweep_report() { return g_report; }
+
+    void write_report(const sweep_report &report, fs::path directory)
+    {
+        if (!fs::exists(directory))
+            fs::create_directories(directory);
+        const std::string stem = "throughput(trial_num=" + std::to_string(CFG.TRIALS_NUMBER) + ",max_sum_prod_iters=" +
+                                 std::to_string(CFG.SUM_PRODUCT_MAX_ITERATIONS) + ",seed=" + std::to_string(CFG.SIMULATION_SEED) + ")";
+        fs::path target = directory / (stem + ".csv");
+        for (size_t dup = 1; fs::exists(target); ++dup)
+            target = directory / (stem + "_" + std::to_string(dup) + ".csv");
+        std::ofstream out(target, std::ios::out | std::ios::trunc);
+        out << "SIM;MATRIX_FILENAME;M;N;QBER;FRAMES;SECONDS;FRAMES_PER_S;SIFTED_MBIT_PER_S;FRAME_ITERATIONS;MEAN_ITERATIONS;"
+               "EFFICIENCY_F;LEAKED_BITS_PER_FRAME;GPUS;PRECISION\n";
+        const std::string precision = CFG.DEVICE_PRECISION == 32 ? (CFG.DEVICE_FP32_FAST ? "fp32-fast" : "fp32") : "fp64";
+        for (const point_report &p : report.points)
+        {
+            const double q = p.exact_qber, h2 = -q * std::log2(q) - (1. - q) * std::log2(1. - q);
+            const double fps = p.seconds > 0 ? p.frames / p.seconds : 0.;
+            out << p.sim_number << ";" << p.matrix_filename << ";" << p.num_check_nodes << ";" << p.num_bit_nodes << ";" << q << ";" << p.frames << ";"
+                << p.seconds << ";" << fps << ";" << fps * p.num_bit_nodes / 1e6 << ";" << p.frame_iterations << ";"
+                << static_cast<double>(p.frame_iterations) / p.frames << ";" << (static_cast<double>(p.num_check_nodes) / p.num_bit_nodes) / h2 << ";"
+                << p.num_check_nodes << ";" << report.gpus << ";" << precision << "\n";
+        }
+    }
+
+    std::vector<std::string> matrix_warnings(const H_matrix &h)
+    {
+        std::vector<std::string> w;
+        size_t unsorted_bits = 0, unsorted_checks = 0, dup = 0;
+        for (size_t i = 0; i < h.num_bit_nodes; ++i)
+            for (int k = 1; k < h.bit_nodes_weight[i]; ++k)
+            {
+                unsorted_bits += h.bit_nodes[i][k] < h.bit_nodes[i][k - 1];
+                dup += h.bit_nodes[i][k] == h.bit_nodes[i][k - 1];
+            }
+        for (size_t j = 0; j < h.num_check_nodes; ++j)
+            for (int k = 1; k < h.check_nodes_weight[j]; ++k)
+                unsorted_checks += h.check_nodes[j][k] < h.check_nodes[j][k - 1];
+        if (unsorted_bits || unsorted_checks)
+            w.push_back("adjacency lists are not sorted ascending (" + std::to_string(unsorted_bits) + " bit-list and " + std::to_string(unsorted_checks) +
+                        " check-list inversions): the reference routes messages by arrival order, which is only the intended routing for sorted lists");
+        if (dup)
+            w.push_back(std::to_string(dup) + " duplicate entries in the bit lists (a double edge cancels in the syndrome but not in the decoder)");
+        return w;
+    }
 }
 
 // CSV, byte for byte the reference's format (default ostream precision, ';' separated, FER = 1 - ratio_ldpc).
@@ -198,6 +243,8 @@ void prepare_sim_inputs(const std::vector<fs::path> &matrix_paths, std::vector<s
         else
             read_sparse_alist_matrix(matrix_paths[i], in.matrix);
         in.matrix_path = matrix_paths[i];
+        for (const std::string &warning : qkd_b200::matrix_warnings(in.matrix))
+            std::cerr << "WARNING (" << matrix_paths[i].filename().string() << "): " << warning << "\n";
         const double code_rate = 1. - (static_cast<double>(in.matrix.num_check_nodes) / in.matrix.num_bit_nodes);
         in.QBER = get_rate_based_QBER_range(code_rate, CFG.R_QBER_PARAMETERS);
     }
@@ -334,6 +381,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
 
     std::vector<sim_result> sim_results(points_total);
     size_t curr_sim = 0, frames_total = 0, iterations_total = 0;
+    g_report = qkd_b200::sweep_report{};
     try
     {
         for (const sim_input &in : sim_in)
@@ -346,6 +394,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
             {
                 if (static_cast<size_t>(n * QBER) == 0)
                     key_too_small(n); // the reference throws from inside the first trial (src/simulation.cpp:170-175)
+                const auto t_point = clock::now();
                 for (auto &st : gpu_stats)
                     std::fill(st.begin(), st.end(), 0);
                 batches_done = 0;
@@ -440,6 +489,16 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 r.ratio_trials_successful_sp = static_cast<double>(ok_sp) / trials;
                 frames_total += trials;
                 iterations_total += reduced[max_it + 4];
+                qkd_b200::point_report pr;
+                pr.sim_number = curr_sim;
+                pr.matrix_filename = matrix_filename;
+                pr.num_bit_nodes = matrix.num_bit_nodes;
+                pr.num_check_nodes = matrix.num_check_nodes;
+                pr.exact_qber = r.initial_QBER;
+                pr.frames = trials;
+                pr.frame_iterations = reduced[max_it + 4];
+                pr.seconds = std::chrono::duration<double>(clock::now() - t_point).count();
+                g_report.points.push_back(pr);
                 ++curr_sim;
             }
         }

@@ -107,6 +107,25 @@ def test_cpp_config_validation(sim, tmp_path):
     assert p.returncode != 0 and "Configuration file not found" in p.stderr
 
 
+def test_cpp_matrix_warnings(sim, tmp_path, lib):
+    """An alist file with an unsorted list loads (as in the reference) but is flagged; the device layout then rejects it
+    because the reference's positional routing would misroute on it."""
+    mat = codes.load_npz("dense_n7_m3")
+    bad = tmp_path / "alist_sparse_matrices"
+    bad.mkdir()
+    codes.write_alist(mat, bad / "h.txt")
+    lines = (bad / "h.txt").read_text().splitlines()
+    parts = lines[4 + 6].split()            # bit 7 is in checks 1 2 3: swap two entries
+    parts[0], parts[1] = parts[1], parts[0]
+    lines[4 + 6] = " ".join(parts)
+    (bad / "h.txt").write_text("\n".join(lines) + "\n")
+    (tmp_path / "config.json").write_text(json.dumps(base_cfg(trials_number=4, code_rate_QBER_parameters=[
+        {"code_rate": 0.58, "QBER_begin": 0.15, "QBER_end": 0.35, "QBER_step": 0.1}])))
+    p = run(sim, tmp_path, check=False)
+    assert "not sorted ascending" in p.stderr
+    assert p.returncode != 0
+
+
 def test_cpp_no_gpu_fails_loudly(sim, tmp_path, lib):
     if lib.qlb_device_count() > 0:
         pytest.skip("a GPU is present")
@@ -123,9 +142,15 @@ def test_sweep_csv_equals_reference_north_star(sim, tmp_path, device_keys):
     trial seeds (default) or by host threads."""
     d = make_dir(tmp_path, base_cfg(device_generate_keys=device_keys), NS, False)
     run(sim, d)
-    out = sorted((d / "results").glob("*.csv"))
+    out = sorted((d / "results").glob("ldpc*.csv"))
     assert len(out) == 1 and out[0].name == "ldpc(trial_num=64,max_sum_prod_iters=100,seed=777).csv"
     assert out[0].read_text() == (GOLD / "sweep_n10240_t64_seed777.csv").read_text()
+    # the side report (never mixed into the reference-format CSV): throughput, efficiency f = (1-R)/h2(q), leakage = M
+    rep = [ln.split(";") for ln in sorted((d / "results").glob("throughput*.csv"))[0].read_text().splitlines()]
+    assert rep[0][:6] == ["SIM", "MATRIX_FILENAME", "M", "N", "QBER", "FRAMES"] and len(rep) == 10
+    import math
+    q = float(rep[1][4]); h2 = -q * math.log2(q) - (1 - q) * math.log2(1 - q)
+    assert abs(float(rep[1][11]) - (5231 / 10240) / h2) < 1e-3 and rep[1][12] == "5231" and rep[1][5] == "64" and float(rep[1][7]) > 0
 
 
 @pytest.mark.gpu
@@ -135,11 +160,11 @@ def test_sweep_csv_equals_reference_dense_n7(sim, tmp_path):
                    code_rate_QBER_parameters=[{"code_rate": 0.58, "QBER_begin": 0.15, "QBER_end": 0.35, "QBER_step": 0.1}])
     d = make_dir(tmp_path, cfg, "dense_n7_m3", True)
     run(sim, d)
-    out = sorted((d / "results").glob("*.csv"))
+    out = sorted((d / "results").glob("ldpc*.csv"))
     assert out[0].read_text() == (GOLD / "sweep_dense_n7_t1000_seed777.csv").read_text()
     # a second run must not overwrite: the reference de-duplicates the file name
     run(sim, d)
-    assert len(sorted((d / "results").glob("*.csv"))) == 2
+    assert len(sorted((d / "results").glob("ldpc*.csv"))) == 2
 
 
 @pytest.mark.gpu
@@ -151,7 +176,7 @@ def test_sweep_fp32_and_forced_allreduce(sim, tmp_path, monkeypatch):
     env = dict(os.environ, QKD_B200_FORCE_ALLREDUCE="1")
     p = subprocess.run([str(sim), str(d)], capture_output=True, text=True, env=env)
     assert p.returncode == 0, p.stderr
-    got = [ln.split(";") for ln in sorted((d / "results").glob("*.csv"))[0].read_text().splitlines()[1:]]
+    got = [ln.split(";") for ln in sorted((d / "results").glob("ldpc*.csv"))[0].read_text().splitlines()[1:]]
     want = [ln.split(";") for ln in (GOLD / "sweep_n10240_t64_seed777.csv").read_text().splitlines()[1:]]
     for g, w in zip(got, want):
         assert g[:7] == w[:7] and g[11:] == w[11:], (g, w)          # identity columns, success ratios, FER
