@@ -148,6 +148,18 @@ int qlb_sum_product_batch(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_p
                           const double *llr, const int32_t *syndrome, int32_t *bits_out, uint32_t *iterations_out,
                           uint8_t *result_out);
 
+/* Trace form of ONE fp64 decode: what the reference prints under CFG.TRACE_SUM_PRODUCT / TRACE_SUM_PRODUCT_LLR
+ * (src/qkd_ldpc_algorithm.cpp:214-327, 246-255 "E", 268-276 "L"/"z", 279-283 "s", 317-327 "M"), copied out per iteration
+ * for the first `capacity` iterations (clamped to max_iterations). llr[n], syndrome[m] as in qlb_sum_product_batch.
+ *   e_out[t][E]  check_to_bit_msg after the clamp, rows = bits in order, row i = its weight(i) slots in arrival order
+ *   l_out[t][n]  total_bit_llr;  z_out[t][n] hard decision;  s_out[t][m] its syndrome
+ *   m_out[t][E]  bit_to_check_msg after the clamp, rows = checks in order (not produced for the converging iteration)
+ * E = number of edges; any of e/l/z/s/m_out and bits_out[n] may be NULL. precision must be QLB_PRECISION_F64. The
+ * decision, iteration count and result equal qlb_sum_product_batch's on the same frame. */
+int qlb_sum_product_trace(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, const double *llr,
+                          const int32_t *syndrome, int32_t capacity, double *e_out, double *l_out, int32_t *z_out,
+                          int32_t *s_out, double *m_out, int32_t *bits_out, uint32_t *iterations_out, uint8_t *result_out);
+
 /* ---- reconciliation ----------------------------------------------------------------------------
  * Replaces QKD_LDPC_regular / QKD_LDPC_irregular (src/qkd_ldpc_algorithm.cpp:347-396 / 398-447) for a
  * batch: per frame, prior +-ln((1-q)/q) from Bob's bits, Alice's syndrome, decode, key compare --

@@ -162,6 +162,9 @@ class Restatement:
         L.orc_syndrome.argtypes = [gp, _i32p, _i32p]
         L.orc_sum_product_f64.argtypes = [gp, _f64p, _i32p, C.c_uint64, C.c_int, C.c_double, _i32p]
         L.orc_sum_product_f64.restype = _SP
+        L.orc_sum_product_f64_trace.argtypes = [gp, _f64p, _i32p, C.c_uint64, C.c_int, C.c_double, C.c_uint64, _f64p, _f64p,
+                                                _i32p, _i32p, _f64p, _i32p]
+        L.orc_sum_product_f64_trace.restype = _SP
         L.orc_sum_product_f32.argtypes = [gp, _f32p, _i32p, C.c_uint64, C.c_int, C.c_float, C.c_int, _i32p]
         L.orc_sum_product_f32.restype = _SP
         L.orc_qkd_ldpc.argtypes = [gp, _i32p, _i32p, C.c_double, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int,
@@ -193,6 +196,20 @@ class Restatement:
             r = self.lib.orc_sum_product_f32(C.byref(g._c), np.ascontiguousarray(llr, np.float32), syn, max_it,
                                              int(enable_thr), thr, f32_form, out)
         return int(r.iterations_num), bool(r.syndromes_match), out
+
+    def sum_product_trace(self, g: Graph, llr, syndrome, capacity, max_it=100, thr=100.0, enable_thr=True):
+        """fp64 decode with the reference's TRACE_SUM_PRODUCT intermediates for the first `capacity` iterations."""
+        cap = min(int(capacity), int(max_it))
+        rows = max(cap, 1)
+        e, m = np.zeros((rows, g.e), np.float64), np.zeros((rows, g.e), np.float64)
+        tot = np.zeros((rows, g.n), np.float64)
+        z, s = np.zeros((rows, g.n), np.int32), np.zeros((rows, g.m), np.int32)
+        out = np.zeros(g.n, np.int32)
+        r = self.lib.orc_sum_product_f64_trace(C.byref(g._c), np.ascontiguousarray(llr, np.float64),
+                                               np.ascontiguousarray(syndrome, np.int32), max_it, int(enable_thr), thr, cap,
+                                               e.reshape(-1), tot.reshape(-1), z.reshape(-1), s.reshape(-1), m.reshape(-1), out)
+        return dict(E=e[:cap], L=tot[:cap], z=z[:cap], s=s[:cap], M=m[:cap], bits=out, iterations=int(r.iterations_num),
+                    result=int(r.syndromes_match))
 
     def qkd_ldpc(self, g: Graph, alice, bob, qber, max_it=100, thr=100.0, enable_thr=True, precision=64,
                  f32_form=F32_LEAVE_ONE_OUT):

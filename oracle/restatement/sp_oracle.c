@@ -28,11 +28,22 @@ int orc_arrays_equal(const int32_t *a, const int32_t *b, size_t n)
     return 1;
 }
 
+/* Optional copy-out of the per-iteration intermediates the reference prints under CFG.TRACE_SUM_PRODUCT
+ * (ref: src/qkd_ldpc_algorithm.cpp:251-255 E, :268-276 L and z, :279-283 s, :317-321 M); fp64 only. */
+typedef struct orc_trace_sink {
+    uint64_t cap;
+    double *e, *l, *m;
+    int32_t *z, *s;
+} orc_trace_sink;
+static __thread orc_trace_sink *g_trace = NULL;
+
 #define REAL double
 #define SP_TANH tanh
 #define SP_ATANH atanh
 #define SP_NAME sp_decode_f64
+#define SP_TRACE g_trace
 #include "sp_decode_body.inc"
+#undef SP_TRACE
 #undef REAL
 #undef SP_TANH
 #undef SP_ATANH
@@ -42,11 +53,24 @@ int orc_arrays_equal(const int32_t *a, const int32_t *b, size_t n)
 #define SP_TANH tanhf
 #define SP_ATANH atanhf
 #define SP_NAME sp_decode_f32
+#define SP_TRACE ((orc_trace_sink *)NULL)
 #include "sp_decode_body.inc"
+#undef SP_TRACE
 #undef REAL
 #undef SP_TANH
 #undef SP_ATANH
 #undef SP_NAME
+
+orc_sp_result orc_sum_product_f64_trace(const orc_graph *g, const double *llr, const int32_t *syndrome, uint64_t max_it,
+                                        int enable_threshold, double thr, uint64_t capacity, double *e_out, double *l_out,
+                                        int32_t *z_out, int32_t *s_out, double *m_out, int32_t *bits_out)
+{
+    orc_trace_sink sink = {capacity, e_out, l_out, m_out, z_out, s_out};
+    g_trace = &sink;
+    const orc_sp_result r = sp_decode_f64(g, llr, syndrome, max_it, enable_threshold, thr, ORC_F32_DIVIDE, bits_out);
+    g_trace = NULL;
+    return r;
+}
 
 orc_sp_result orc_sum_product_f64(const orc_graph *g, const double *llr, const int32_t *syndrome, uint64_t max_it,
                                   int enable_threshold, double thr, int32_t *bits_out)

@@ -58,6 +58,13 @@ int orc_arrays_equal(const int32_t *a, const int32_t *b, size_t n);
 orc_sp_result orc_sum_product_f64(const orc_graph *g, const double *llr, const int32_t *syndrome,
                                   uint64_t max_it, int enable_threshold, double thr, int32_t *bits_out);
 
+/* The same decode with the intermediates the reference prints under CFG.TRACE_SUM_PRODUCT copied out for the first
+ * `capacity` iterations (ref: src/qkd_ldpc_algorithm.cpp:251-255 E[capacity][e] bit-major, :268-276 L[..][n] and z[..][n],
+ * :279-283 s[..][m], :317-321 M[..][e] check-major; M is not produced for the converging iteration). Any sink may be NULL. */
+orc_sp_result orc_sum_product_f64_trace(const orc_graph *g, const double *llr, const int32_t *syndrome, uint64_t max_it,
+                                        int enable_threshold, double thr, uint64_t capacity, double *e_out, double *l_out,
+                                        int32_t *z_out, int32_t *s_out, double *m_out, int32_t *bits_out);
+
 /* Same schedule in single precision (statistical comparator for the fp32 kernels). */
 orc_sp_result orc_sum_product_f32(const orc_graph *g, const float *llr, const int32_t *syndrome,
                                   uint64_t max_it, int enable_threshold, float thr, int form, int32_t *bits_out);

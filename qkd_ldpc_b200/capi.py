@@ -25,7 +25,7 @@ EXPORTS = [
     "qlb_code_gather_wavefronts",
     "qlb_ctx_create", "qlb_ctx_destroy", "qlb_ctx_device", "qlb_ctx_sm_count", "qlb_ctx_stream", "qlb_ctx_synchronize",
     "qlb_ctx_counters", "qlb_ctx_timer_start", "qlb_ctx_timer_stop",
-    "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch",
+    "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch", "qlb_sum_product_trace",
     "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device", "qlb_stats_allreduce",
     "qlb_generate_batch_packed", "qlb_generate_device", "qlb_run_trials",
 ]
@@ -88,6 +88,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.qlb_syndrome_batch.argtypes = [vp, vp, i64, vp, vp]
     lib.qlb_syndrome_batch_packed.argtypes = [vp, vp, i64, vp, vp]
     lib.qlb_sum_product_batch.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp]
+    lib.qlb_sum_product_trace.argtypes = [vp, vp, pp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_reconcile_batch.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_reconcile_batch_packed.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.qlb_reconcile_device.argtypes = [vp, vp, pp, i64, vp, vp, vp, vp, vp, vp, vp]
@@ -239,6 +240,24 @@ class Context:
         _check(self.lib, self.lib.qlb_sum_product_batch(self.handle, code.handle, C.byref(params), f, _ptr(llr), _ptr(syn),
                                                         _ptr(bits), _ptr(it), _ptr(res)))
         return it, res, bits
+
+    def sum_product_trace(self, code: Code, params: DecodeParams, llr, syndrome, capacity: int):
+        """One fp64 frame with the reference's TRACE_SUM_PRODUCT intermediates per iteration.
+        Returns dict(E, L, z, s, M, bits, iterations, result); E/M are [capacity][edges] in the reference's row order."""
+        llr = np.ascontiguousarray(llr, np.float64).reshape(code.n)
+        syn = np.ascontiguousarray(syndrome, np.int32).reshape(code.m)
+        cap = min(int(capacity), int(params.max_iterations))
+        e = np.zeros((cap, code.e), np.float64)
+        m = np.zeros((cap, code.e), np.float64)
+        tot = np.zeros((cap, code.n), np.float64)
+        z = np.zeros((cap, code.n), np.int32)
+        s = np.zeros((cap, code.m), np.int32)
+        bits = np.zeros(code.n, np.int32)
+        it = np.zeros(1, np.uint32)
+        res = np.zeros(1, np.uint8)
+        _check(self.lib, self.lib.qlb_sum_product_trace(self.handle, code.handle, C.byref(params), _ptr(llr), _ptr(syn), cap,
+                                                        _ptr(e), _ptr(tot), _ptr(z), _ptr(s), _ptr(m), _ptr(bits), _ptr(it), _ptr(res)))
+        return dict(E=e, L=tot, z=z, s=s, M=m, bits=bits, iterations=int(it[0]), result=int(res[0]))
 
     def reconcile(self, code: Code, params: DecodeParams, alice, bob, qber, want_decoded=True, want_syndrome=False):
         alice = np.ascontiguousarray(np.atleast_2d(alice), np.int32)

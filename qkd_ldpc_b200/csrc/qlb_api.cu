@@ -3,6 +3,7 @@
 // entry that does work launches the sm_100a kernels in qlb_kernels.cuh or fails.
 #include "qlb_internal.hpp"
 #include "qlb_generate.cuh"
+#include "qlb_trace_f64.cuh"
 #include "qlb_layout.hpp"
 
 #include <atomic>
@@ -661,6 +662,87 @@ extern "C"
         QLB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (bits_out)
             unpack_frames(ctx->host_pack_out.data(), n_frames, L.n, L.words_n, bits_out);
+        return QLB_OK;
+    }
+
+    // ---- trace form of one decode (qlb_trace_f64.cuh) ------------------------------------------------------------------
+    int qlb_sum_product_trace(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, const double *llr,
+                              const int32_t *syndrome, int32_t capacity, double *e_out, double *l_out, int32_t *z_out,
+                              int32_t *s_out, double *m_out, int32_t *bits_out, uint32_t *iterations_out, uint8_t *result_out)
+    {
+        if (!ctx || !code || capacity < 0)
+            return fail(QLB_ERR_INVALID, "qlb_sum_product_trace: null context/code or negative capacity");
+        int rc = check_params(params);
+        if (rc)
+            return rc;
+        if (params->precision != QLB_PRECISION_F64)
+            return fail(QLB_ERR_UNSUPPORTED, "qlb_sum_product_trace: the trace exists for the reference's arithmetic (fp64) only");
+        if (!llr || !syndrome || !iterations_out || !result_out)
+            return fail(QLB_ERR_INVALID, "qlb_sum_product_trace: null host buffer");
+        const CodeLayout &L = code->L;
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const CodeDev *dev;
+        if ((rc = get_device_code(ctx, code, &dev)))
+            return rc;
+        if (capacity > params->max_iterations)
+            capacity = params->max_iterations;
+        const size_t slots = (size_t)L.slots, n = (size_t)L.n, m = (size_t)L.m, cap = (size_t)capacity;
+        // device scratch: msg[slots] | snap_e[cap][slots] | snap_m[cap][slots] | tot[cap][n] (doubles) | z_cur[n] | z[cap][n] | s[cap][m] (int32)
+        const size_t n_f64 = slots + 2 * cap * slots + cap * n, n_i32 = n + cap * n + cap * m;
+        QLB_CUDA(ctx->scratch.reserve(n_f64 * 8 + n_i32 * 4));
+        double *d_msg = static_cast<double *>(ctx->scratch.p), *d_e = d_msg + slots, *d_m = d_e + cap * slots, *d_tot = d_m + cap * slots;
+        int32_t *d_zcur = reinterpret_cast<int32_t *>(d_tot + cap * n), *d_z = d_zcur + n, *d_s = d_z + cap * n;
+        ctx->host_pack_a.resize(L.words_m);
+        pack_frames(syndrome, 1, L.m, L.words_m, ctx->host_pack_a.data());
+        QLB_CUDA(ctx->in_llr.reserve(n * 8));
+        QLB_CUDA(ctx->in_syn.reserve((size_t)L.words_m * 4));
+        QLB_CUDA(ctx->out_it.reserve(4));
+        QLB_CUDA(ctx->out_res.reserve(1));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_llr.p, llr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(ctx->in_syn.p, ctx->host_pack_a.data(), (size_t)L.words_m * 4, cudaMemcpyHostToDevice, ctx->stream));
+        QLB_CUDA(cudaMemsetAsync(d_msg, 0, n_f64 * 8 + n_i32 * 4, ctx->stream));
+        trace_f64_kernel<<<1, kTraceThreads, 0, ctx->stream>>>(*dev, (const double *)ctx->in_llr.p, (const uint32_t *)ctx->in_syn.p,
+                                                                params->max_iterations, params->enable_threshold, params->threshold,
+                                                                capacity, d_msg, d_zcur, d_e, d_m, d_tot, d_z, d_s,
+                                                                (uint32_t *)ctx->out_it.p, (uint8_t *)ctx->out_res.p);
+        QLB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+        std::vector<double> h_e(e_out ? cap * slots : 0), h_m(m_out ? cap * slots : 0);
+        std::vector<int32_t> h_z(bits_out ? n : 0);
+        if (e_out && cap)
+            QLB_CUDA(cudaMemcpyAsync(h_e.data(), d_e, cap * slots * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (m_out && cap)
+            QLB_CUDA(cudaMemcpyAsync(h_m.data(), d_m, cap * slots * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (l_out && cap)
+            QLB_CUDA(cudaMemcpyAsync(l_out, d_tot, cap * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (z_out && cap)
+            QLB_CUDA(cudaMemcpyAsync(z_out, d_z, cap * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (s_out && cap)
+            QLB_CUDA(cudaMemcpyAsync(s_out, d_s, cap * m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (bits_out)
+            QLB_CUDA(cudaMemcpyAsync(bits_out, d_zcur, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(iterations_out, ctx->out_it.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaMemcpyAsync(result_out, ctx->out_res.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        // slot snapshots -> the reference's jagged rows (plain re-indexing, no arithmetic)
+        const size_t E = (size_t)L.e;
+        for (size_t t = 0; t < cap; ++t)
+        {
+            if (e_out) // check_to_bit_msg[i][a]: bit-major, a-th arrival at bit i
+            {
+                size_t q = 0;
+                for (size_t i = 0; i < n; ++i)
+                    for (int a = 0; a < L.max_bit_w; ++a)
+                    {
+                        const uint32_t sl = L.bit_slots[(size_t)a * n + i];
+                        if (sl != kNoSlot)
+                            e_out[t * E + q++] = h_e[t * slots + sl];
+                    }
+            }
+            if (m_out) // bit_to_check_msg[j][k]: check-major, CSR order
+                for (size_t q = 0; q < E; ++q)
+                    m_out[t * E + q] = h_m[t * slots + L.slot_of_edge[q]];
+        }
         return QLB_OK;
     }
 

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "qkd_ldpc.hpp"
+#include "trace_print.hpp"
 
 config_data CFG;
 
@@ -123,8 +124,14 @@ int main(int argc, char **argv)
         CFG = get_config_data(root / "config.json");
         const fs::path matrix_dir = root / (CFG.USE_DENSE_MATRICES ? "dense_matrices" : "alist_sparse_matrices");
         if (CFG.INTERACTIVE_MODE)
-            throw std::runtime_error("interactive_mode is not part of this build (single-frame stdin UI; run the batch mode)");
-        std::cout << "BATCH MODE\n";
+        {
+            qkd_b200::print_coloured(qkd_b200::colour::purple, "INTERACTIVE MODE\n");
+            QKD_LDPC_interactive_simulation(matrix_dir);
+            qkd_b200::release_device_state();
+            return EXIT_SUCCESS;
+        }
+        qkd_b200::print_coloured(qkd_b200::colour::purple, "BATCH MODE\n");
+        std::fflush(stdout);
         const std::vector<fs::path> matrix_paths = get_file_paths_in_directory(matrix_dir);
         if (matrix_paths.empty())
             throw std::runtime_error("Matrix folder is empty: " + matrix_dir.string());

@@ -8,7 +8,9 @@
 //   SP_result, LDPC_result, sum_product_decoding_*, QKD_LDPC_*                    src/qkd_ldpc_algorithm.hpp:14-31
 //   config_data, CFG, get_config_data                                             src/config.hpp:14-67
 //   sim_input, trial_result, sim_result, run_trial, QKD_LDPC_batch_simulation,
-//   prepare_sim_inputs, get_rate_based_QBER_range, write_file                     src/simulation.hpp:16-50
+//   prepare_sim_inputs, get_rate_based_QBER_range, write_file,
+//   QKD_LDPC_interactive_simulation                                               src/simulation.hpp:16-50
+//   console traces under CFG.TRACE_QKD_LDPC / TRACE_SUM_PRODUCT / TRACE_SUM_PRODUCT_LLR   src/qkd_ldpc_algorithm.cpp:214-327,407-442
 //
 // There is no CPU decoder behind these functions: they throw std::runtime_error when no B200 is usable.
 #pragma once
@@ -138,6 +140,9 @@ std::vector<double> get_rate_based_QBER_range(const double code_rate, const std:
 void prepare_sim_inputs(const std::vector<fs::path> &matrix_paths, std::vector<sim_input> &sim_inputs_out);
 trial_result run_trial(const H_matrix &matrix, const double QBER, size_t seed);
 std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &sim_in);
+fs::path select_matrix_file(const std::vector<fs::path> &matrix_paths);  // src/utils.hpp:18
+void QKD_LDPC_interactive_simulation(fs::path matrix_dir_path);          // src/simulation.hpp:46
+// print_array / print_regular_matrix / print_irregular_matrix (src/utils.hpp:15-46) live in trace_print.hpp
 
 // ---- implementation hooks (not in the reference) -----------------------------------------------------------------------
 namespace qkd_b200

@@ -23,6 +23,7 @@
 
 #include "device_bridge.hpp"
 #include "qkd_ldpc.hpp"
+#include "trace_print.hpp"
 
 namespace
 {
@@ -250,6 +251,70 @@ void prepare_sim_inputs(const std::vector<fs::path> &matrix_paths, std::vector<s
     }
 }
 
+// One frame per QBER value of the matrix picked on stdin, printed step by step: the reference's interactive mode
+// (src/simulation.cpp:73-137, src/utils.cpp:50-67), each frame decoded on the GPU.
+fs::path select_matrix_file(const std::vector<fs::path> &matrix_paths)
+{
+    using qkd_b200::colour;
+    qkd_b200::print_coloured(colour::green, "Choose file: \n");
+    for (size_t i = 0; i < matrix_paths.size(); i++)
+        qkd_b200::print_coloured(colour::green, std::to_string(i + 1) + ". " + matrix_paths[i].filename().string() + "\n");
+    std::fflush(stdout);
+    int file_index = 0;
+    std::cin >> file_index;
+    file_index -= 1;
+    if (file_index < 0 || file_index >= static_cast<int>(matrix_paths.size()))
+        throw std::runtime_error("Wrong file number.");
+    return matrix_paths[file_index];
+}
+
+void QKD_LDPC_interactive_simulation(fs::path matrix_dir_path)
+{
+    using qkd_b200::colour;
+    using qkd_b200::print_coloured;
+    H_matrix matrix;
+    const std::vector<fs::path> matrix_paths = get_file_paths_in_directory(matrix_dir_path);
+    const fs::path matrix_path = select_matrix_file(matrix_paths);
+    if (CFG.USE_DENSE_MATRICES)
+        read_dense_matrix(matrix_path, matrix);
+    else
+        read_sparse_alist_matrix(matrix_path, matrix);
+    try
+    {
+        print_coloured(colour::green, std::string(matrix.is_regular ? "Matrix H is regular." : "Matrix H is irregular.") + "\n");
+        const size_t n = matrix.num_bit_nodes;
+        std::vector<int> alice(n), bob(n);
+        XoshiroCpp::Xoshiro256PlusPlus prng(CFG.SIMULATION_SEED); // one stream for all frames, as in the reference (:95)
+        const double code_rate = 1. - (static_cast<double>(matrix.num_check_nodes) / matrix.num_bit_nodes);
+        const std::vector<double> QBER = get_rate_based_QBER_range(code_rate, CFG.R_QBER_PARAMETERS);
+        for (size_t i = 0; i < QBER.size(); i++)
+        {
+            print_coloured(colour::green, "\u2116:" + std::to_string(i + 1) + "\n");
+            generate_random_bit_array(prng, n, alice.data());
+            const double initial_QBER = introduce_errors(prng, alice.data(), n, QBER[i], bob.data());
+            print_coloured(colour::green, "Actual QBER: " + qkd_b200::format_shortest(initial_QBER) + "\n");
+            if (initial_QBER == 0.)
+                key_too_small(n);
+            int error_num = 0;
+            for (size_t k = 0; k < n; k++)
+                error_num += alice[k] ^ bob[k];
+            print_coloured(colour::green, "Number of errors in a key: " + std::to_string(error_num) + "\n");
+            std::fflush(stdout);
+            const LDPC_result r = matrix.is_regular ? QKD_LDPC_regular(alice.data(), bob.data(), initial_QBER, matrix)
+                                                    : QKD_LDPC_irregular(alice.data(), bob.data(), initial_QBER, matrix);
+            print_coloured(colour::green, "Iterations performed: " + std::to_string(r.sp_res.iterations_num) + "\n");
+            print_coloured(colour::green, std::string(r.keys_match && r.sp_res.syndromes_match ? "Error reconciliation SUCCESSFUL" : "Error reconciliation FAILED") + "\n\n");
+            std::fflush(stdout);
+        }
+    }
+    catch (...)
+    {
+        free_matrix_H(matrix);
+        throw;
+    }
+    free_matrix_H(matrix);
+}
+
 // A single trial (batch of one). Throws like the reference when floor(N * QBER) == 0.
 trial_result run_trial(const H_matrix &matrix, const double QBER, size_t seed)
 {
@@ -312,6 +377,22 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     qlb_code *code = nullptr;                 // the current matrix
     std::atomic<uint64_t> device_ns{0};
     std::vector<std::thread> gpu_threads;
+    // integer statistics of one finished trial: histogram of iterations of successful frames + {n_sp, n_ldpc, n_trials, sum_iterations}
+    auto account = [max_it](std::vector<uint64_t> &st, const trial_result &tr)
+    {
+        const size_t it = tr.ldpc_res.sp_res.iterations_num;
+        if (tr.ldpc_res.sp_res.syndromes_match)
+        {
+            ++st[std::min<size_t>(it, max_it)];
+            ++st[max_it + 1];
+            st[max_it + 2] += tr.ldpc_res.keys_match;
+        }
+        ++st[max_it + 3];
+        st[max_it + 4] += it;
+    };
+    // With any console trace enabled the trials of a point run one after another on this thread through run_trial, so the
+    // output reads like the reference's with threads_number = 1 (its pool would interleave the prints of concurrent trials).
+    const bool traced = CFG.TRACE_QKD_LDPC || CFG.TRACE_SUM_PRODUCT || CFG.TRACE_SUM_PRODUCT_LLR;
     for (int g = 0; g < workers; ++g)
         gpu_threads.emplace_back([&, g]
                                  {
@@ -345,7 +426,6 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                     }
                     else
                     {
-                        std::vector<uint64_t> &st = gpu_stats[g];
                         for (size_t f = 0; f < b->frames; ++f)
                         {
                             trial_result &tr = trial_results[b->first_trial + f];
@@ -353,14 +433,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                             tr.ldpc_res.sp_res.syndromes_match = (b->result[f] & QLB_RES_SYNDROMES_MATCH) != 0;
                             tr.ldpc_res.keys_match = (b->result[f] & QLB_RES_KEYS_MATCH) != 0;
                             tr.initial_QBER = b->qber[f];
-                            if (tr.ldpc_res.sp_res.syndromes_match)
-                            {
-                                ++st[std::min<size_t>(b->iterations[f], max_it)];
-                                ++st[max_it + 1];
-                                st[max_it + 2] += tr.ldpc_res.keys_match;
-                            }
-                            ++st[max_it + 3];
-                            st[max_it + 4] += b->iterations[f];
+                            account(gpu_stats[g], tr);
                         }
                     }
                 }
@@ -399,7 +472,12 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                     std::fill(st.begin(), st.end(), 0);
                 batches_done = 0;
                 size_t issued = 0;
-                for (size_t first = 0; first < trials; first += batch_frames, ++issued)
+                for (size_t k = 0; traced && k < trials; ++k)
+                {
+                    trial_results[k] = run_trial(matrix, QBER, seeds[k] + curr_sim);
+                    account(gpu_stats[0], trial_results[k]);
+                }
+                for (size_t first = 0; !traced && first < trials; first += batch_frames, ++issued)
                 {
                     batch *b = free_batches.pop();
                     b->first_trial = first;
