@@ -15,6 +15,7 @@ QLB_OK = 0
 PRECISION_F64 = 64
 PRECISION_F32 = 32
 FLAG_F32_FAST_MATH = 1
+FLAG_F64_FUSED_RATIO = 2
 RES_SYNDROMES_MATCH = 1
 RES_KEYS_MATCH = 2
 
@@ -116,7 +117,10 @@ def _ptr(a):
 
 
 def make_params(precision=64, max_iterations=100, threshold=100.0, enable_threshold=True, fast_math=False, tier=None):
-    flags = FLAG_F32_FAST_MATH if fast_math else 0
+    if fast_math:  # the cheaper check rule of either precision
+        flags = FLAG_F32_FAST_MATH if int(precision) == 32 else FLAG_F64_FUSED_RATIO
+    else:
+        flags = 0
     if tier is not None:
         flags |= (int(tier) + 1) << 8  # QLB_FLAG_TEST_TIER: force a slower storage tier
     return DecodeParams(int(precision), int(max_iterations), int(bool(enable_threshold)), flags, float(threshold))

@@ -132,6 +132,8 @@ namespace
             return fail(QLB_ERR_INVALID, "Sum-product message LLR threshold must be > 0!");
         if ((p->flags & QLB_FLAG_F32_FAST_MATH) && p->precision != QLB_PRECISION_F32)
             return fail(QLB_ERR_INVALID, "QLB_FLAG_F32_FAST_MATH requires fp32 precision");
+        if ((p->flags & QLB_FLAG_F64_FUSED_RATIO) && p->precision != QLB_PRECISION_F64)
+            return fail(QLB_ERR_INVALID, "QLB_FLAG_F64_FUSED_RATIO requires fp64 precision");
         return QLB_OK;
     }
 
@@ -224,7 +226,7 @@ namespace
         if (forced == 3)
             return fail(QLB_ERR_UNSUPPORTED, "the streaming kernel does not handle this code / precision");
         if (p->precision == QLB_PRECISION_F64 && forced < 0 && resident_f64_eligible(ctx, args.code))
-            return launch_resident_f64(ctx, args, kReconcile);
+            return launch_resident_f64(ctx, args, kReconcile, (p->flags & QLB_FLAG_F64_FUSED_RATIO) != 0);
         if (p->precision == QLB_PRECISION_F64)
             return launch_tier<MathF64, kReconcile>(ctx, args, forced);
         if (fast)

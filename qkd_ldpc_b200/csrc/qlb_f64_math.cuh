@@ -78,6 +78,35 @@ namespace qlb
             return dk * kLn2Hi - ((hfsq - (s * (hfsq + R) + dk * kLn2Lo)) - f);
         }
 
+        // ln(num / den) for 0 < den <= num without forming the quotient: ONE division for the ratio and the logarithm together.
+        // den is rescaled by the power of two 2^j that brings m = num / (den 2^j) into ~[sqrt(1/2), sqrt 2] (exponent difference,
+        // corrected by one through an integer comparison of the leading mantissa bits; the boundary need not be exact, the
+        // polynomial holds a little beyond it). Then s = (m - 1) / (m + 1) = (num - den') / (num + den') -- the numerator is exact
+        // (Sterbenz) -- and ln m = 2 s + s R(s^2) with fdlibm's R (e_log.c: "log(1+f) = 2s + s*R"), result j ln 2 + ln m. <= 2 ulp.
+        // Edge outcomes follow the IEEE results of ln(num / den): den = 0 < num -> +inf, 0 / 0 or a NaN operand -> NaN; a
+        // denominator rounded below zero (only possible when the true ratio exceeds ~2^52) counts as zero.
+        __device__ __forceinline__ double log_ratio(double num, double den)
+        {
+            const bool regular = den > 0. && num > 0.;
+            const double nn = regular ? num : 1., dd = regular ? den : 1.;
+            const int hn = __double2hiint(nn), hd = __double2hiint(dd);
+            int j = (hn >> 20) - (hd >> 20);
+            // leading 16 mantissa bits (with the hidden one) of both: u / d in (1/2, 2)
+            const uint32_t u = (((uint32_t)hn & 0x000fffffu) | 0x00100000u) >> 5, d = (((uint32_t)hd & 0x000fffffu) | 0x00100000u) >> 5;
+            j += (u * 46341u > d * 65536u) ? 1 : 0; // u / d > sqrt 2
+            j -= (u * 65536u < d * 46341u) ? 1 : 0; // u / d < sqrt(1/2)
+            const double ds = __hiloint2double(hd + (j << 20), __double2loint(dd));
+            const double s = div_pos(nn - ds, nn + ds);
+            const double z = s * s, w = z * z;
+            const double t1 = w * fma(w, fma(w, kLg[5], kLg[3]), kLg[1]);
+            const double t2 = z * fma(w, fma(w, fma(w, kLg[6], kLg[4]), kLg[2]), kLg[0]);
+            const double dj = (double)j;
+            double r = fma(dj, kLn2Hi, fma(2., s, fma(s, t2 + t1, dj * kLn2Lo)));
+            r = regular ? r : __longlong_as_double(0x7ff0000000000000LL);                      // den <= 0 < num (or num <= 0 < ... see below)
+            r = (num != num || den != den || !(num > 0.)) ? __longlong_as_double(0x7ff8000000000000LL) : r; // NaN operand, 0/0
+            return r;
+        }
+
         // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped at 64 (the quotient is exactly +-1 far earlier)
         __device__ __forceinline__ double tanh_half(double m)
         {

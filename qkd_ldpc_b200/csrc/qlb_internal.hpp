@@ -117,5 +117,5 @@ namespace qlb
     bool stream_f32_eligible(const CodeDev &c);
     int launch_stream_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);
     bool resident_f64_eligible(const qlb_ctx *ctx, const CodeDev &c);
-    int launch_resident_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile);
+    int launch_resident_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fused);
 }

@@ -140,6 +140,49 @@ namespace qlb
         }
     };
 
+    // fp64, fused-ratio form of the same rule (QLB_FLAG_F64_FUSED_RATIO): with e_j = e^-|m_j|, tanh(|m_j|/2) = (1-e_j)/(1+e_j);
+    // A = prod(1-e_j), B = prod(1+e_j), S = B + A, D = B - A give for edge k
+    //     (1 + row/t_k) / (1 - row/t_k) = (S - e_k D) / (D - e_k S),      2 atanh(row / t_k) = ln of that,
+    // so an edge costs one exp, ONE division and one log polynomial (f64m::log_ratio) instead of exp + three divisions + log:
+    // ~35 % fewer FP64 instructions. The reference's special outcomes are kept: a zero message (t_k = 0) gives NaN on its own
+    // edge and 0 on the others, a saturated product gives +-inf (then the clamp), a NaN input floods the check. D carries
+    // an absolute rounding error of ~2^-52 B, so -- like the reference's own tanh, which rounds to exactly 1 beyond |m| ~ 37.4
+    // (:220-226) -- magnitudes above ~36 are quantised and then saturate; the two saturate at slightly different places, which
+    // is why this form is opt-in and carries its own parity campaign (profiles/parity_r01.md) instead of replacing MathF64.
+    struct MathF64Fused
+    {
+        typedef double real;
+        template <int W>
+        static __device__ __forceinline__ void check(double (&v)[W], int w, bool s, bool en, double thr)
+        {
+            double e[W];
+            double A = 1., B = 1.;
+            int neg = s ? 1 : 0;
+            bool poisoned = false;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                if (k < w)
+                {
+                    poisoned |= v[k] != v[k];
+                    neg ^= (int)((uint32_t)__double2hiint(v[k]) >> 31);
+                    e[k] = f64m::exp_neg(-fmin(fabs(v[k]), 64.));
+                    A *= 1. - e[k];
+                    B *= 1. + e[k];
+                }
+            const double S = B + A, D = B - A;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                if (k < w)
+                {
+                    const double num = fma(-e[k], D, S), den = fma(-e[k], S, D);
+                    double mag = f64m::log_ratio(num, den);
+                    mag = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : mag;
+                    const int sg = neg ^ (int)((uint32_t)__double2hiint(v[k]) >> 31);
+                    v[k] = clamp_msg(sg ? -mag : mag, thr, en);
+                }
+        }
+    };
+
     // fp32 with libdevice tanhf/atanhf and a leave-one-out product (prefix * suffix), which cannot produce the 0/0 the
     // divide form hits in single precision (SURVEY.md 8a "fp32 note").
     struct MathF32

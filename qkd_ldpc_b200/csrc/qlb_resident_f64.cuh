@@ -41,7 +41,7 @@ namespace qlb
 
     // All checks of weight exactly W in [lo, hi). zsrc: packed bits whose parity per check is wanted (the last hard decision,
     // or Alice's key during the first pass, which yields her syndrome: src/qkd_ldpc_algorithm.cpp:413-414).
-    template <int W>
+    template <typename Math, int W>
     __device__ __forceinline__ uint32_t check_segment64(int kThreads, const Split64 &msg, const DecodeArgs &args, const uint16_t *__restrict__ col_of_slot,
                                                         const uint32_t *__restrict__ zsrc, uint32_t lo, uint32_t hi, uint32_t &my_syn, int &rbit,
                                                         bool first, bool en, double thr)
@@ -72,7 +72,7 @@ namespace qlb
                 sb = (my_syn >> rbit) & 1u;
                 bad |= par ^ sb; // calculate_syndrome + arrays_equal of :277-298, one iteration late
             }
-            MathF64::check<W>(v, W, sb != 0, en, thr);
+            Math::template check<W>(v, W, sb != 0, en, thr);
 #pragma unroll
             for (int k = 0; k < W; ++k)
                 msg.st(args.code.base[k] + p, v[k]);
@@ -81,7 +81,7 @@ namespace qlb
     }
 
     // kBW: uniform bit weight. Host-checked: slots < 65535, n < 65536, max_check_w <= 8, n % 32 == 0, n, m <= 32 * kThreads.
-    template <bool kReconcile, int kBW, int kMaxThreads>
+    template <typename Math, bool kReconcile, int kBW, int kMaxThreads>
     __global__ void __launch_bounds__(kMaxThreads, 1) decode_resident_f64_kernel(const DecodeArgs args, uint32_t smem_slots,
                                                                                  const uint16_t *__restrict__ col_of_slot)
     {
@@ -213,7 +213,7 @@ namespace qlb
                         const uint32_t lo = s_seg_lo[sg], hi = s_seg_hi[sg];
                         switch (s_seg_w[sg])
                         {
-#define QLB_SEG64(W_) case W_: bad |= check_segment64<W_>(kThreads, msg, args, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); break;
+#define QLB_SEG64(W_) case W_: bad |= check_segment64<Math, W_>(kThreads, msg, args, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); break;
                             QLB_SEG64(1) QLB_SEG64(2) QLB_SEG64(3) QLB_SEG64(4) QLB_SEG64(5) QLB_SEG64(6) QLB_SEG64(7) QLB_SEG64(8)
 #undef QLB_SEG64
                         default: // checks without edges: satisfied only by a zero syndrome bit

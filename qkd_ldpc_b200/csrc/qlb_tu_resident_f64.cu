@@ -19,10 +19,10 @@ namespace
                (size_t)ctx->smem_optin > kResident64StaticSmem + resident64_small_bytes(c.n, c.m) + 8192 &&
                resident64_smem_slots(ctx, c) >= (uint32_t)c.slots / 2;
     }
-    template <bool kReconcile, int kBW>
+    template <typename Math, bool kReconcile, int kBW>
     int launch_resident64(qlb_ctx *ctx, DecodeArgs &args)
     {
-        auto kern = decode_resident_f64_kernel<kReconcile, kBW, kResident64Threads>;
+        auto kern = decode_resident_f64_kernel<Math, kReconcile, kBW, kResident64Threads>;
         int kThreads = balanced_block_size(args.code, kResident64Threads, 0.85);
         if (const char *e = std::getenv("QLB_RES64_THREADS")) // experiments only
         {
@@ -51,14 +51,14 @@ namespace
         ++ctx->launches;
         return QLB_OK;
     }
-    template <bool kReconcile>
+    template <typename Math, bool kReconcile>
     int launch_resident64_bw(qlb_ctx *ctx, DecodeArgs &args)
     {
         switch (args.code.uniform_bit_w)
         {
-        case 2: return launch_resident64<kReconcile, 2>(ctx, args);
-        case 3: return launch_resident64<kReconcile, 3>(ctx, args);
-        case 4: return launch_resident64<kReconcile, 4>(ctx, args);
+        case 2: return launch_resident64<Math, kReconcile, 2>(ctx, args);
+        case 3: return launch_resident64<Math, kReconcile, 3>(ctx, args);
+        case 4: return launch_resident64<Math, kReconcile, 4>(ctx, args);
         default: return fail(QLB_ERR_UNSUPPORTED, "fp64 resident kernel: unsupported bit weight");
         }
     }
@@ -66,8 +66,10 @@ namespace
 namespace qlb
 {
     bool resident_f64_eligible(const qlb_ctx *ctx, const CodeDev &c) { return resident64_eligible_impl(ctx, c); }
-    int launch_resident_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile)
+    int launch_resident_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fused)
     {
-        return reconcile ? launch_resident64_bw<true>(ctx, args) : launch_resident64_bw<false>(ctx, args);
+        if (fused)
+            return reconcile ? launch_resident64_bw<MathF64Fused, true>(ctx, args) : launch_resident64_bw<MathF64Fused, false>(ctx, args);
+        return reconcile ? launch_resident64_bw<MathF64, true>(ctx, args) : launch_resident64_bw<MathF64, false>(ctx, args);
     }
 }

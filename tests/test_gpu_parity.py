@@ -40,9 +40,11 @@ def test_syndrome_bit_exact(ctx, dev_codes, graphs, oracle, name):
         assert (_unpack(got_p, g.m) == want).all()
 
 
-def test_golden_frames_fp64(ctx, dev_codes, frames):
+@pytest.mark.parametrize("fused", [False, True])
+def test_golden_frames_fp64(ctx, dev_codes, frames, fused):
+    """fused: QLB_FLAG_F64_FUSED_RATIO, the one-division form of the fp64 check rule -- held to the same per-frame bar."""
     code = dev_codes[NS]
-    p = capi.make_params(64, int(frames["max_it"]), float(frames["thr"]), True)
+    p = capi.make_params(64, int(frames["max_it"]), float(frames["thr"]), True, fast_math=fused)
     it, res, dec, syn = ctx.reconcile_packed(code, p, frames["alice"].view(np.uint32), frames["bob"].view(np.uint32),
                                              frames["q_exact"], want_decoded=True, want_syndrome=True)
     wm = code.words_m
@@ -83,12 +85,13 @@ def waterfall(oracle):
     return _waterfall_inputs(oracle, 10240)
 
 
-def test_waterfall_fp64_matches_reference_per_frame(ctx, dev_codes, waterfall):
+@pytest.mark.parametrize("fused", [False, True])
+def test_waterfall_fp64_matches_reference_per_frame(ctx, dev_codes, waterfall, fused):
     """672 frames across the waterfall (q = 0.05 ... 0.09): iterations, flags and decoded bits must all equal the reference."""
     from oracle.bindings import fnv1a64_bits
     A, B, Q, R, H = waterfall
     code = dev_codes[NS]
-    p = capi.make_params(64, 100, 100.0, True)
+    p = capi.make_params(64, 100, 100.0, True, fast_math=fused)
     it, res, dec, _ = ctx.reconcile_packed(code, p, capi.pack_bits(A), capi.pack_bits(B), Q)
     assert (it == R[:, 0]).all(), f"{int((it != R[:, 0]).sum())} frames differ in iteration count"
     assert ((res & 1) == R[:, 1]).all() and (((res >> 1) & 1) == R[:, 2]).all()
@@ -113,7 +116,7 @@ def test_waterfall_fp32_statistical(ctx, dev_codes, waterfall, fast):
     assert (it[ok & same_flags] == R[ok & same_flags, 0]).mean() > 0.95
 
 
-@pytest.mark.parametrize("precision,fast", [(64, False), (32, False), (32, True)])
+@pytest.mark.parametrize("precision,fast", [(64, False), (64, True), (32, False), (32, True)])
 def test_sweep_grid_identical(ctx, dev_codes, oracle, graphs, precision, fast):
     """On the benchmark's QBER grid (0.03 ... 0.11) every frame must decode as the fp64 reference does."""
     g, code = graphs[NS], dev_codes[NS]
@@ -219,12 +222,13 @@ def test_edge_cases(ctx, dev_codes, graphs, oracle, frames):
         it, res, dec, _ = ctx.reconcile_packed(code, capi.make_params(64, mi, 100.0, True), a, b, q)
         assert it[0] == want[0] and bool(res[0] & 1) == want[1] and bool(res[0] & 2) == want[2]
         assert (_unpack(dec, g.n)[0] == want[4]).all()
-    # clamp disabled (inf/NaN semantics) and a small clamp
+    # clamp disabled (inf/NaN semantics) and a small clamp; both forms of the fp64 check rule
     for en, thr in ((False, 100.0), (True, 5.0), (True, 20.0)):
         want = oracle.qkd_ldpc(g, A, B, float(q[0]), max_it=30, thr=thr, enable_thr=en)
-        it, res, dec, _ = ctx.reconcile_packed(code, capi.make_params(64, 30, thr, en), a, b, q)
-        assert it[0] == want[0] and bool(res[0] & 1) == want[1], (en, thr, it, want[:3])
-        assert (_unpack(dec, g.n)[0] == want[4]).all()
+        for fused in (False, True):
+            it, res, dec, _ = ctx.reconcile_packed(code, capi.make_params(64, 30, thr, en, fast_math=fused), a, b, q)
+            assert it[0] == want[0] and bool(res[0] & 1) == want[1], (en, thr, fused, it, want[:3])
+            assert (_unpack(dec, g.n)[0] == want[4]).all(), (en, thr, fused)
     # invalid QBER
     with pytest.raises(capi.QlbError) as ei:
         ctx.reconcile_packed(code, p, a, b, np.array([0.0]))
