@@ -132,7 +132,7 @@ def run_reference_arm(args, guard):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    tpp = args.cpu_trials_per_point or max(16, cores)
+    tpp = args.cpu_trials_per_point or max(64, 4 * cores)  # ~2 s wall = ~30 core-seconds per sweep
     grid = qber_grid()
     for _ in range(args.warmup):
         cpu_reference_sweep(max(1, tpp // 8), cores)
@@ -394,7 +394,7 @@ def main():
     fer_parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        tpp = args.cpu_trials_per_point or max(16, cores)
+        tpp = args.cpu_trials_per_point or max(64, 4 * cores)  # ~2 s wall = ~30 core-seconds per sweep
         kind, sec, outs = cpu_reference_sweep(tpp, cores)
         cpu_val = tpp * len(grid) / sec
         cpu = {"value": cpu_val, "unit": "frames/s", "cores": cores, "kind": kind, "seconds": sec,

@@ -4,6 +4,7 @@ There is no CPU implementation behind these classes: a missing library or a miss
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from pathlib import Path
 
@@ -57,7 +58,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else _build.LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("QLB_LIBRARY") or _build.LIB_PATH)  # QLB_LIBRARY: kernel-tuning experiments
     if not p.exists():
         _build.build_library()
     lib = C.CDLL(str(p))

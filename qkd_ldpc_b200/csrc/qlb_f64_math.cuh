@@ -6,7 +6,7 @@
 // operand), have no branches, and are specialised to the argument ranges the decoder produces:
 //   exp_neg(x)   x in [-64, 0]           Cody-Waite reduction by ln 2 (round-to-nearest through the 1.5*2^52 shift), degree-13
 //                                        Taylor polynomial in Horner form, exponent insertion by integer add.  <= 1 ulp
-//   div_pos(a,d) d > 0, 2^-60 < d < 2^60 MUFU.RCP seed (fp32), two Newton steps, one residual correction.      correctly rounded
+//   div_pos(a,d) d > 0, 2^-60 < d < 2^60 MUFU.RCP seed (fp32), one Newton step, one residual correction.       correctly rounded
 //                                        on every sampled input
 //   log_pos(y)   y >= 2^-60, finite      the classical fdlibm scheme: y = 2^k m, m in [sqrt(1/2), sqrt 2), s = f/(2+f), f = m-1,
 //                                        log m = f - (f^2/2 - s (f^2/2 + R(s^2))), R = the degree-14 minimax polynomial
@@ -43,16 +43,16 @@ namespace qlb
             return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
         }
 
+        // MUFU.RCP seed (relative error <= 2^-22) and ONE Newton step: y = (1/d)(1 + eps), |eps| <= 2^-44
         __device__ __forceinline__ double rcp_pos(double d)
         {
             float y0;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__double2float_rn(d)));
-            double y = (double)y0;
-            double e = fma(-d, y, 1.0);
-            y = fma(y, e, y);
-            e = fma(-d, y, 1.0);
-            return fma(y, e, y);
+            const double y = (double)y0;
+            return fma(y, fma(-d, y, 1.0), y);
         }
+        // q = a y is 44 bits good; the residual a - d q is exact in an FMA and |residual * y| carries a relative error of 2^-44
+        // again, so the corrected quotient is the rounding of a / d + O(2^-88): a second Newton step on y would buy nothing.
         __device__ __forceinline__ double div_pos(double a, double d)
         {
             const double y = rcp_pos(d);
@@ -83,28 +83,23 @@ namespace qlb
         // corrected by one through an integer comparison of the leading mantissa bits; the boundary need not be exact, the
         // polynomial holds a little beyond it). Then s = (m - 1) / (m + 1) = (num - den') / (num + den') -- the numerator is exact
         // (Sterbenz) -- and ln m = 2 s + s R(s^2) with fdlibm's R (e_log.c: "log(1+f) = 2s + s*R"), result j ln 2 + ln m. <= 2 ulp.
-        // Edge outcomes follow the IEEE results of ln(num / den): den = 0 < num -> +inf, 0 / 0 or a NaN operand -> NaN; a
-        // denominator rounded below zero (only possible when the true ratio exceeds ~2^52) counts as zero.
+        // (the special outcomes are selected by the caller from `num`, `den`: for operands outside 0 < den <= num the value
+        // returned here is meaningless, but nothing traps)
         __device__ __forceinline__ double log_ratio(double num, double den)
         {
-            const bool regular = den > 0. && num > 0.;
-            const double nn = regular ? num : 1., dd = regular ? den : 1.;
-            const int hn = __double2hiint(nn), hd = __double2hiint(dd);
+            const int hn = __double2hiint(num), hd = __double2hiint(den);
             int j = (hn >> 20) - (hd >> 20);
             // leading 16 mantissa bits (with the hidden one) of both: u / d in (1/2, 2)
             const uint32_t u = (((uint32_t)hn & 0x000fffffu) | 0x00100000u) >> 5, d = (((uint32_t)hd & 0x000fffffu) | 0x00100000u) >> 5;
             j += (u * 46341u > d * 65536u) ? 1 : 0; // u / d > sqrt 2
             j -= (u * 65536u < d * 46341u) ? 1 : 0; // u / d < sqrt(1/2)
-            const double ds = __hiloint2double(hd + (j << 20), __double2loint(dd));
-            const double s = div_pos(nn - ds, nn + ds);
+            const double ds = __hiloint2double(hd + (j << 20), __double2loint(den));
+            const double s = div_pos(num - ds, num + ds);
             const double z = s * s, w = z * z;
             const double t1 = w * fma(w, fma(w, kLg[5], kLg[3]), kLg[1]);
             const double t2 = z * fma(w, fma(w, fma(w, kLg[6], kLg[4]), kLg[2]), kLg[0]);
             const double dj = (double)j;
-            double r = fma(dj, kLn2Hi, fma(2., s, fma(s, t2 + t1, dj * kLn2Lo)));
-            r = regular ? r : __longlong_as_double(0x7ff0000000000000LL);                      // den <= 0 < num (or num <= 0 < ... see below)
-            r = (num != num || den != den || !(num > 0.)) ? __longlong_as_double(0x7ff8000000000000LL) : r; // NaN operand, 0/0
-            return r;
+            return fma(dj, kLn2Hi, fma(2., s, fma(s, t2 + t1, dj * kLn2Lo)));
         }
 
         // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped at 64 (the quotient is exactly +-1 far earlier)

@@ -85,11 +85,16 @@ namespace qlb
     // weight segment of the sorted checks with stride T, and the block waits for the slowest thread, so T is chosen to keep the
     // last round of each walk as full as possible (`check_share`: the check walk's share of an iteration); among equally balanced
     // sizes the smaller block measured slightly faster (B200, N=10240: 768 > 896 > 1024 threads by 2 %). Both walks must stay within the 32 per-thread rounds the kernels park bits for.
-    inline int balanced_block_size(const CodeDev &c, int max_threads, double check_share)
+    // `min_threads`: the fp64 kernel is latency-bound (dependent DFMA chains, L2 index loads) and wants warps more than balance:
+    // measured on B200, N=10240, fused rule: 384 / 512 / 640 / 768 threads = 3.08 / 3.46 / 3.61 / 3.87 M frame-iterations/s
+    // (`size_bias` > 0: among equally balanced sizes the larger block).
+    inline int balanced_block_size(const CodeDev &c, int max_threads, double check_share, int min_threads = 0, double size_bias = -0.02)
     {
         int best = 0;
         double best_score = -1.;
-        for (int t = max_threads; t >= max_threads / 2 && t >= 32; t -= 32)
+        if (min_threads <= 0)
+            min_threads = max_threads / 2;
+        for (int t = max_threads; t >= min_threads && t >= 32; t -= 32)
         {
             long long check_rounds = 0;
             for (int w = c.max_check_w; w >= 0; --w)
@@ -101,7 +106,7 @@ namespace qlb
             if (check_rounds > 32 || bit_rounds > 32)
                 break;
             const double ec = (double)c.m / t / (double)check_rounds, eb = (double)c.n / t / (double)bit_rounds;
-            const double score = (check_share * ec + (1. - check_share) * eb) * (1. - 0.02 * t / max_threads);
+            const double score = (check_share * ec + (1. - check_share) * eb) * (1. + size_bias * t / max_threads);
             if (score > best_score + 1e-12)
             {
                 best_score = score;

@@ -174,11 +174,21 @@ namespace qlb
             for (int k = 0; k < W; ++k)
                 if (k < w)
                 {
+                    // num >= den by construction, so den > 0 is the regular case. Otherwise the IEEE outcomes of ln(num / den):
+                    // den <= 0 < num (a saturated product; a denominator rounded below zero counts as zero) -> +inf, which the
+                    // clamp then turns into thr (:246-249); 0 / 0 (the message on this edge was exactly 0) or a NaN -> NaN.
                     const double num = fma(-e[k], D, S), den = fma(-e[k], S, D);
-                    double mag = f64m::log_ratio(num, den);
-                    mag = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : mag;
+                    const double r = f64m::log_ratio(num, den);
+                    const bool ok = den > 0. && !poisoned, to_inf = num > 0. && den <= 0. && !poisoned;
+                    int hi = ok ? __double2hiint(r) : (to_inf ? 0x7ff00000 : 0x7ff80000);
+                    int lo = ok ? __double2loint(r) : 0;
+                    if (en && __hiloint2double(hi, lo) > thr) // the magnitude is >= 0 or NaN (a NaN passes the clamp, :508-524)
+                    {
+                        hi = __double2hiint(thr);
+                        lo = __double2loint(thr);
+                    }
                     const int sg = neg ^ (int)((uint32_t)__double2hiint(v[k]) >> 31);
-                    v[k] = clamp_msg(sg ? -mag : mag, thr, en);
+                    v[k] = __hiloint2double(hi ^ (sg << 31), lo);
                 }
         }
     };

@@ -73,17 +73,17 @@ namespace qlb
     }
 
     // One check of weight exactly W for the VEC frames of this lane.
+    // row_stride: floats between the rows of consecutive slots (G, or B * G when B groups are interleaved slot by slot)
     template <typename Rule, int W, int VEC>
     __device__ __forceinline__ void stream_check(float *__restrict__ msg, const CodeDev &code, uint32_t p, int lane, uint32_t *__restrict__ synT,
-                                                 float cap, bool first, uint32_t (&bad)[VEC])
+                                                 float cap, bool first, uint32_t (&bad)[VEC], size_t row_stride = 32 * VEC)
     {
-        constexpr int G = 32 * VEC;
         float v[VEC][W];
         float *row[W];
 #pragma unroll
         for (int k = 0; k < W; ++k)
         {
-            row[k] = msg + ((size_t)(code.base[k] + p) * G + VEC * lane);
+            row[k] = msg + ((size_t)(code.base[k] + p) * row_stride + VEC * lane);
             float t[VEC];
             VecIO<VEC>::load(row[k], t);
 #pragma unroll

@@ -1,0 +1,553 @@
+// Phase-split form of the frame-interleaved streaming decoder (qlb_stream_f32.cuh): same data layout (msg[slot][G], keys and
+// decisions bit-transposed per group), same node arithmetic (stream_check, the resident kernel's rules), but every pass of
+// the flooding schedule is its own kernel over ALL groups of the launch:
+//
+//     setup | check(0) update(0) bit | check(1) update(1) bit | ... | check(max_it) update(max_it) | finalize
+//
+// Why: the persistent one-CTA-per-group kernel ties a group to one SM for its whole life -- it needs as many groups as SMs
+// (N = 1 000 000: HBM holds 99 groups, so 49 SMs idle), the last groups of a launch run on a mostly empty chip, and one
+// register budget (128) has to serve both passes, capping the bit pass at 16 warps per SM although it is pure gather/scatter.
+// Here work items are (group, chunk of consecutive nodes), spread evenly over a grid sized to the SM count; the check kernel
+// and the bit kernel each get the register count and occupancy that suits them, kernel boundaries are the grid barriers, and
+// groups whose frames have all converged drop out of the work list (group-granular active-frame compaction; converged
+// frames inside a live group are frozen as before). No host synchronisation: every kernel reads the number of live
+// groups from device memory and returns at once when it is zero.
+// Bundles: B groups share one message array, interleaved slot by slot (msg[slot][B][G]), and the B rows of a slot are
+// handled by adjacent warps of one CTA. The bit pass is a random gather of rows; with B = 4 the unit the DRAM sees is 2 KB
+// instead of 512 B (measured on B200, N = 100 000: bit kernel 3.4 TB/s at B = 1 against 5.4 TB/s for the sequential check
+// kernel -- row-buffer locality, not occupancy, is what the gather lacks). Bookkeeping stays per group.
+// Results are bit-identical to the persistent kernel and to the SM-resident kernel (tests/test_gpu_codes.py).
+#pragma once
+#include "qlb_stream_f32.cuh"
+
+namespace qlb
+{
+    // tuning knobs (compile-time so that each kernel gets its own register budget); defaults = best measured on B200
+#ifndef QLB_SPLIT_CHECK_THREADS
+#define QLB_SPLIT_CHECK_THREADS 256
+#endif
+#ifndef QLB_SPLIT_CHECK_MINB
+#define QLB_SPLIT_CHECK_MINB 2
+#endif
+#ifndef QLB_SPLIT_BIT_THREADS
+#define QLB_SPLIT_BIT_THREADS 256
+#endif
+#ifndef QLB_SPLIT_BIT_MINB
+#define QLB_SPLIT_BIT_MINB 4
+#endif
+#ifndef QLB_SPLIT_BIT_U
+#define QLB_SPLIT_BIT_U 2 // bits per warp in flight
+#endif
+    constexpr int kSplitCheckThreads = QLB_SPLIT_CHECK_THREADS, kSplitBitThreads = QLB_SPLIT_BIT_THREADS, kSplitSetupThreads = 512;
+    constexpr int kSplitCheckChunk = 8 * (kSplitCheckThreads / 32); // sorted check positions per work item
+    constexpr int kSplitBitChunk = 16 * (kSplitBitThreads / 32);    // bits per work item
+
+    struct SplitState
+    {
+        unsigned char *bundles; // per bundle: the interleaved message array, then the B per-group carves (split_small_carve)
+        size_t bundle_stride;
+        uint32_t *act;  // [n_groups][4] word j, bit l: frame VEC*l + j of the group still decoding
+        uint32_t *bad;  // [n_groups][4] same indexing: some check of that frame failed in the last check pass
+        uint32_t *succ; // [n_groups][4] frames whose decisions satisfied the syndrome
+        uint32_t *list; // [n_bundles] bundles with a live group, [0, *n_live)
+        uint32_t *n_live;
+        long long group0; // index of this wave's first group in the whole batch (frame = (group0 + g) * G + ...)
+        int n_groups;
+        int bundle; // B: groups per bundle (1, 2, 4 or 8; divides the warps per CTA of the pass kernels)
+    };
+
+    // per-group arrays other than the messages (bytes)
+    struct SplitSmall
+    {
+        size_t bobT, aliceT, zT, synT, total;
+    };
+    __host__ __device__ inline SplitSmall split_small_carve(int n, int m, int vec)
+    {
+        SplitSmall c{};
+        size_t o = 0;
+        c.bobT = o; o += align_up((size_t)n * vec * 4, 256);
+        c.aliceT = o; o += align_up((size_t)n * vec * 4, 256);
+        c.zT = o; o += align_up((size_t)n * vec * 4, 256);
+        c.synT = o; o += align_up((size_t)m * vec * 4, 256);
+        c.total = o;
+        return c;
+    }
+    __host__ __device__ inline size_t split_bundle_bytes(int n, int m, int slots, int vec, int bundle)
+    {
+        return align_up((size_t)slots * bundle * 32 * vec * 4, 256) + (size_t)bundle * split_small_carve(n, m, vec).total;
+    }
+
+    struct SplitGroup
+    {
+        float *msg;        // row of slot s for this group: msg + s * row_stride (+ VEC * lane)
+        size_t row_stride; // B * G floats
+        uint32_t *bobT, *aliceT, *zT, *synT;
+    };
+    __device__ __forceinline__ SplitGroup split_group(const SplitState &st, const CodeDev &code, int vec, uint32_t g)
+    {
+        const int B = st.bundle, G = 32 * vec;
+        const uint32_t bu = g / (uint32_t)B, gb = g % (uint32_t)B;
+        const SplitSmall cv = split_small_carve(code.n, code.m, vec);
+        unsigned char *p = st.bundles + (size_t)bu * st.bundle_stride;
+        unsigned char *small = p + align_up((size_t)code.slots * B * G * 4, 256) + (size_t)gb * cv.total;
+        SplitGroup r;
+        r.msg = reinterpret_cast<float *>(p) + (size_t)gb * G;
+        r.row_stride = (size_t)B * G;
+        r.bobT = reinterpret_cast<uint32_t *>(small + cv.bobT);
+        r.aliceT = reinterpret_cast<uint32_t *>(small + cv.aliceT);
+        r.zT = reinterpret_cast<uint32_t *>(small + cv.zT);
+        r.synT = reinterpret_cast<uint32_t *>(small + cv.synT);
+        return r;
+    }
+
+    // weight segments of the sorted checks into shared memory (thread 0), as in the other kernels
+    __device__ __forceinline__ int split_segments(const CodeDev &code, uint32_t *s_seg_w, uint32_t *s_seg_lo, uint32_t *s_seg_hi)
+    {
+        int ns = 0;
+        for (int w = code.max_check_w; w >= 0; --w)
+        {
+            const uint32_t lo = (w < code.max_check_w) ? code.cnt[w] : 0u, hi = (w > 0) ? code.cnt[w - 1] : (uint32_t)code.m;
+            if (lo < hi)
+            {
+                s_seg_w[ns] = (uint32_t)w;
+                s_seg_lo[ns] = lo;
+                s_seg_hi[ns] = hi;
+                ++ns;
+            }
+        }
+        return ns;
+    }
+
+    // ---- set-up: transposed keys, priors into the messages, frame bookkeeping; one CTA per group at a time -------------------
+    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    __global__ void __launch_bounds__(kSplitSetupThreads) stream_setup_kernel(const DecodeArgs args, const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        constexpr int kWarps = kSplitSetupThreads / 32;
+        const CodeDev &code = args.code;
+        const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const float unit = Rule::kUnit;
+        for (uint32_t g = blockIdx.x; g < (uint32_t)st.n_groups; g += gridDim.x)
+        {
+            const SplitGroup sg = split_group(st, code, VEC, g);
+            const long long f0 = (st.group0 + g) * G;
+            float lp[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                const long long f = f0 + (long long)VEC * lane + j;
+                lp[j] = (kReconcile && f < args.n_frames) ? unit * (float)args.log_prior[f] : 0.f;
+            }
+            if (kReconcile)
+            {
+                transpose_in<VEC>(args.bob, f0, args.n_frames, code.words_n, n, sg.bobT);
+                transpose_in<VEC>(args.alice, f0, args.n_frames, code.words_n, n, sg.aliceT);
+            }
+            else
+            {
+                transpose_in<VEC>(args.syndrome_in, f0, args.n_frames, code.words_m, m, sg.aliceT);
+                __syncthreads();
+                for (int p = tid; p < m; p += kSplitSetupThreads)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        sg.synT[(size_t)p * VEC + j] = sg.aliceT[(size_t)code.check_order[p] * VEC + j];
+            }
+            __syncthreads();
+            for (int i = warp; i < n; i += kWarps)
+            {
+                float pv[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    float prior;
+                    uint32_t abit = 0;
+                    if (kReconcile)
+                    {
+                        const uint32_t bb = (sg.bobT[(size_t)i * VEC + j] >> lane) & 1u;
+                        abit = (sg.aliceT[(size_t)i * VEC + j] >> lane) & 1u;
+                        prior = __uint_as_float(__float_as_uint(lp[j]) ^ (bb << 31));
+                    }
+                    else
+                    {
+                        const long long f = f0 + (long long)VEC * lane + j;
+                        prior = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
+                    }
+                    pv[j] = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
+                }
+#pragma unroll
+                for (int a = 0; a < kBW; ++a)
+                    VecIO<VEC>::store(sg.msg + ((size_t)code.bit_slots32[(size_t)a * n + i] * sg.row_stride + VEC * lane), pv);
+                if (lane == 0)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        sg.zT[(size_t)i * VEC + j] = 0;
+            }
+            if (warp == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    const long long f = f0 + (long long)VEC * lane + j;
+                    const bool live = f < args.n_frames;
+                    if (live)
+                        args.iterations[f] = (uint32_t)args.max_it;
+                    const uint32_t word = __ballot_sync(0xffffffffu, live);
+                    if (lane == 0)
+                    {
+                        st.act[g * 4 + j] = word;
+                        st.bad[g * 4 + j] = 0;
+                        st.succ[g * 4 + j] = 0;
+                    }
+                }
+                if (lane == 0 && g % (uint32_t)st.bundle == 0)
+                    st.list[g / (uint32_t)st.bundle] = g / (uint32_t)st.bundle;
+            }
+            __syncthreads();
+        }
+        if (blockIdx.x == 0 && tid == 0)
+            *st.n_live = (uint32_t)((st.n_groups + st.bundle - 1) / st.bundle);
+    }
+
+    // ---- check pass over the live bundles: work item = (bundle, kSplitCheckChunk consecutive sorted checks) -------------------
+    template <typename Rule, bool kReconcile, int VEC>
+    __global__ void __launch_bounds__(kSplitCheckThreads, QLB_SPLIT_CHECK_MINB) stream_check_kernel(const DecodeArgs args, const SplitState st, int it)
+    {
+        constexpr int kWarps = kSplitCheckThreads / 32;
+        __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
+        const uint32_t n_live = *st.n_live;
+        if (n_live == 0)
+            return;
+        const CodeDev &code = args.code;
+        const int m = code.m, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0)
+            split_segments(code, s_seg_w, s_seg_lo, s_seg_hi);
+        __syncthreads();
+        const float cap = args.cap_f32 * Rule::kUnit;
+        const bool first = kReconcile && it == 0;
+        const uint32_t chunks = ((uint32_t)m + kSplitCheckChunk - 1) / kSplitCheckChunk;
+        const unsigned long long items = (unsigned long long)n_live * chunks;
+        const int B = st.bundle, step = kWarps / B; // adjacent warps: the B groups of the bundle on the same check
+        for (unsigned long long item = blockIdx.x; item < items; item += gridDim.x)
+        {
+            const uint32_t g = st.list[item / chunks] * (uint32_t)B + (uint32_t)(warp % B);
+            const uint32_t p0 = (uint32_t)(item % chunks) * kSplitCheckChunk, p1 = min((uint32_t)m, p0 + kSplitCheckChunk);
+            if (g >= (uint32_t)st.n_groups)
+                continue;
+            uint32_t alive = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                alive |= st.act[g * 4 + j];
+            if (!alive)
+                continue; // every frame of this group has converged: its rows are left alone
+            const SplitGroup sg = split_group(st, code, VEC, g);
+            float *__restrict__ msg = sg.msg;
+            const size_t rs = sg.row_stride;
+            uint32_t bad[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                bad[j] = 0;
+            int s = 0;
+#pragma unroll 1
+            for (uint32_t p = p0 + warp / B; p < p1; p += step)
+            {
+                while (p >= s_seg_hi[s])
+                    ++s;
+                if (p + step < p1) // the rows of this warp's next check -> L2 while this one is computed (cnt[k]: checks with an edge position k)
+                    for (int k = 0; k < (int)s_seg_w[s]; ++k)
+                        if (p + step < code.cnt[k])
+                            prefetch_l2(msg + ((size_t)(code.base[k] + p + step) * rs + VEC * lane));
+                switch (s_seg_w[s])
+                {
+#define QLB_PSEG(W_) case W_: stream_check<Rule, W_, VEC>(msg, code, p, lane, sg.synT, cap, first, bad, rs); break;
+                    QLB_PSEG(1) QLB_PSEG(2) QLB_PSEG(3) QLB_PSEG(4) QLB_PSEG(5) QLB_PSEG(6) QLB_PSEG(7) QLB_PSEG(8)
+                    QLB_PSEG(9) QLB_PSEG(10) QLB_PSEG(11) QLB_PSEG(12) QLB_PSEG(13) QLB_PSEG(14) QLB_PSEG(15) QLB_PSEG(16)
+#undef QLB_PSEG
+                default: // a check without edges is satisfied only by a zero syndrome bit
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                    {
+                        if (first)
+                        {
+                            if (lane == 0)
+                                sg.synT[(size_t)p * VEC + j] = 0;
+                        }
+                        else
+                            bad[j] |= (sg.synT[(size_t)p * VEC + j] >> lane) & 1u;
+                    }
+                    break;
+                }
+            }
+            if (!first)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    const uint32_t word = __ballot_sync(0xffffffffu, bad[j] & 1u);
+                    if (lane == 0 && word)
+                        atomicOr(&st.bad[g * 4 + j], word);
+                }
+        }
+    }
+
+    // ---- frame bookkeeping between the check pass and the bit pass of round `it` (one small CTA) ----------------------------------
+    // Frames whose last decisions satisfied every check are done (src/qkd_ldpc_algorithm.cpp:285-298): iterations = it. Groups
+    // without a live frame leave the work list.
+    template <int VEC>
+    __global__ void __launch_bounds__(1024) stream_update_kernel(const DecodeArgs args, const SplitState st, int it)
+    {
+        constexpr int G = 32 * VEC;
+        __shared__ uint32_t s_count;
+        if (*st.n_live == 0)
+            return;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if (threadIdx.x == 0)
+            s_count = 0;
+        __syncthreads();
+        const int B = st.bundle;
+        const uint32_t n_bundles = (uint32_t)((st.n_groups + B - 1) / B);
+        for (uint32_t bu = warp; bu < n_bundles; bu += nwarps)
+        {
+            // lane = 4 * (group within the bundle) + word j
+            const uint32_t g = bu * (uint32_t)B + (uint32_t)(lane >> 2);
+            const int j = lane & 3;
+            uint32_t a = 0;
+            if ((lane >> 2) < B && j < VEC && g < (uint32_t)st.n_groups)
+            {
+                a = st.act[g * 4 + j];
+                const uint32_t b = st.bad[g * 4 + j];
+                if (it > 0 && a)
+                {
+                    uint32_t done = a & ~b;
+                    if (done)
+                    {
+                        st.succ[g * 4 + j] |= done;
+                        a &= ~done;
+                        st.act[g * 4 + j] = a;
+                        while (done)
+                        {
+                            const int l = __ffs(done) - 1;
+                            done &= done - 1;
+                            args.iterations[(st.group0 + g) * G + (long long)VEC * l + j] = (uint32_t)it;
+                        }
+                    }
+                }
+                st.bad[g * 4 + j] = 0;
+            }
+            const uint32_t any = __ballot_sync(0xffffffffu, a != 0);
+            if (lane == 0 && any)
+                st.list[atomicAdd(&s_count, 1u)] = bu;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            *st.n_live = s_count;
+    }
+
+    // ---- bit pass over the live bundles: work item = (bundle, kSplitBitChunk consecutive bits), U bits per warp in flight -----------
+    template <bool kReconcile, int kBW, int VEC, int U>
+    __device__ __forceinline__ void split_bits(const DecodeArgs &args, const SplitGroup &sg, const int (&bit)[U], int lane, const float (&lp)[VEC],
+                                               const uint32_t (&act_word)[VEC], long long f0, float unit, float cap, bool clamp_b2c)
+    {
+        const CodeDev &code = args.code;
+        const int n = code.n;
+        float *row[U][kBW];
+        float c[U][kBW][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+                row[u][a] = sg.msg + ((size_t)code.bit_slots32[(size_t)a * n + bit[u]] * sg.row_stride + VEC * lane);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+                VecIO<VEC>::load(row[u][a], c[u][a]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const int i = bit[u];
+            float total[VEC];
+            uint32_t zbits = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                float prior;
+                if (kReconcile)
+                    prior = __uint_as_float(__float_as_uint(lp[j]) ^ (((sg.bobT[(size_t)i * VEC + j] >> lane) & 1u) << 31));
+                else
+                {
+                    const long long f = f0 + (long long)VEC * lane + j;
+                    prior = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
+                }
+                float t = prior;
+#pragma unroll
+                for (int a = 0; a < kBW; ++a)
+                    t = t + c[u][a][j];
+                total[j] = t;
+                zbits |= (uint32_t)(t <= 0.f) << j;
+            }
+#pragma unroll
+            for (int a = 0; a < kBW; ++a)
+            {
+                float o[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    float v = total[j] - c[u][a][j];
+                    if (clamp_b2c)
+                        v = fminf(fmaxf(v, -cap), cap);
+                    o[j] = __uint_as_float((__float_as_uint(v) & ~1u) | ((zbits >> j) & 1u));
+                }
+                VecIO<VEC>::store(row[u][a], o);
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                const uint32_t word = __ballot_sync(0xffffffffu, (zbits >> j) & 1u);
+                if (lane == 0)
+                {
+                    const size_t at = (size_t)i * VEC + j;
+                    sg.zT[at] = (sg.zT[at] & ~act_word[j]) | (word & act_word[j]); // converged frames keep their decision
+                }
+            }
+        }
+    }
+
+    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    __global__ void __launch_bounds__(kSplitBitThreads, QLB_SPLIT_BIT_MINB) stream_bit_kernel(const DecodeArgs args, const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        constexpr int kWarps = kSplitBitThreads / 32;
+        const uint32_t n_live = *st.n_live;
+        if (n_live == 0)
+            return;
+        const CodeDev &code = args.code;
+        const int n = code.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const float unit = Rule::kUnit;
+        const float cap = args.cap_f32 * unit;
+        const bool clamp_b2c = !(Rule::kUnit != 1.f && cap >= 25.f);
+        const uint32_t chunks = ((uint32_t)n + kSplitBitChunk - 1) / kSplitBitChunk;
+        const unsigned long long items = (unsigned long long)n_live * chunks;
+        const int B = st.bundle, step = kWarps / B; // adjacent warps: the B groups of the bundle on the same bit
+        for (unsigned long long item = blockIdx.x; item < items; item += gridDim.x)
+        {
+            const uint32_t g = st.list[item / chunks] * (uint32_t)B + (uint32_t)(warp % B);
+            const int i0 = (int)(item % chunks) * kSplitBitChunk, i1 = min(n, i0 + kSplitBitChunk);
+            if (g >= (uint32_t)st.n_groups)
+                continue;
+            const SplitGroup sg = split_group(st, code, VEC, g);
+            const long long f0 = (st.group0 + g) * G;
+            float lp[VEC];
+            uint32_t act_word[VEC], alive = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                const long long f = f0 + (long long)VEC * lane + j;
+                lp[j] = (kReconcile && f < args.n_frames) ? unit * (float)args.log_prior[f] : 0.f;
+                act_word[j] = st.act[g * 4 + j];
+                alive |= act_word[j];
+            }
+            if (!alive)
+                continue;
+            constexpr int U = QLB_SPLIT_BIT_U;
+            int i = i0 + warp / B;
+#pragma unroll 1
+            for (; i + (U - 1) * step < i1; i += U * step)
+            {
+                int many[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    many[u] = i + u * step;
+                split_bits<kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, f0, unit, cap, clamp_b2c);
+            }
+#pragma unroll 1
+            for (; i < i1; i += step)
+            {
+                const int one[1] = {i};
+                split_bits<kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, f0, unit, cap, clamp_b2c);
+            }
+        }
+    }
+
+    // ---- results: flags, key comparison, decoded keys and syndromes back in frame-major order; one CTA per group at a time ----
+    template <bool kReconcile, int VEC>
+    __global__ void __launch_bounds__(kSplitSetupThreads) stream_finalize_kernel(const DecodeArgs args, const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        constexpr int kWarps = kSplitSetupThreads / 32;
+        __shared__ uint32_t s_flags[kWarps][4];
+        const CodeDev &code = args.code;
+        const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        for (uint32_t g = blockIdx.x; g < (uint32_t)st.n_groups; g += gridDim.x)
+        {
+            const SplitGroup sg = split_group(st, code, VEC, g);
+            const long long f0 = (st.group0 + g) * G;
+            uint32_t differs = 0;
+            if (kReconcile)
+            {
+                uint32_t d[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    d[j] = 0;
+                for (int i = tid; i < n; i += kSplitSetupThreads)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        d[j] |= sg.zT[(size_t)i * VEC + j] ^ sg.aliceT[(size_t)i * VEC + j];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    uint32_t x = d[j];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        x |= __shfl_xor_sync(0xffffffffu, x, o);
+                    if (lane == 0)
+                        s_flags[warp][j] = x;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    uint32_t x = 0;
+                    for (int w = 0; w < kWarps; ++w)
+                        x |= s_flags[w][j];
+                    differs |= ((x >> lane) & 1u) << j;
+                }
+            }
+            if (warp == 0)
+            {
+                unsigned long long it_sum = 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    const long long f = f0 + (long long)VEC * lane + j;
+                    if (f < args.n_frames)
+                    {
+                        uint8_t r = (st.succ[g * 4 + j] >> lane) & 1u ? 1 : 0;
+                        if (kReconcile && !((differs >> j) & 1u))
+                            r |= 2;
+                        args.result[f] = r;
+                        it_sum += args.iterations[f];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    it_sum += __shfl_xor_sync(0xffffffffu, it_sum, o);
+                if (lane == 0)
+                    atomicAdd(args.iter_total, it_sum);
+            }
+            if (args.decoded)
+                transpose_out<VEC>(sg.zT, f0, args.n_frames, code.words_n, n, args.decoded);
+            if (kReconcile && args.syndrome_out)
+                for (int p = warp; p < m; p += kWarps)
+                {
+                    const uint32_t jn = code.check_order[p];
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                    {
+                        const long long f = f0 + (long long)VEC * lane + j;
+                        if (f < args.n_frames && ((sg.synT[(size_t)p * VEC + j] >> lane) & 1u))
+                            atomicOr(&args.syndrome_out[f * code.words_m + (jn >> 5)], 1u << (jn & 31));
+                    }
+                }
+            __syncthreads();
+        }
+    }
+}

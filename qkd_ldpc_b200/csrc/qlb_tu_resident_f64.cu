@@ -15,7 +15,7 @@ namespace
     bool resident64_eligible_impl(const qlb_ctx *ctx, const CodeDev &c)
     {
         return c.slots < 65535 && c.n < 65536 && c.bit_slots16 && c.col_of_slot16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 &&
-               c.max_check_w <= 8 && c.n % 32 == 0 && balanced_block_size(c, kResident64Threads, 0.85) > 0 &&
+               c.max_check_w <= 8 && c.n % 32 == 0 && balanced_block_size(c, kResident64Threads, 0.85, kResident64Threads * 3 / 4, 0.05) > 0 &&
                (size_t)ctx->smem_optin > kResident64StaticSmem + resident64_small_bytes(c.n, c.m) + 8192 &&
                resident64_smem_slots(ctx, c) >= (uint32_t)c.slots / 2;
     }
@@ -23,7 +23,7 @@ namespace
     int launch_resident64(qlb_ctx *ctx, DecodeArgs &args)
     {
         auto kern = decode_resident_f64_kernel<Math, kReconcile, kBW, kResident64Threads>;
-        int kThreads = balanced_block_size(args.code, kResident64Threads, 0.85);
+        int kThreads = balanced_block_size(args.code, kResident64Threads, 0.85, kResident64Threads * 3 / 4, 0.05);
         if (const char *e = std::getenv("QLB_RES64_THREADS")) // experiments only
         {
             const int t = std::atoi(e) / 32 * 32;
@@ -41,8 +41,8 @@ namespace
         args.scratch = static_cast<unsigned char *>(ctx->scratch.p);
         args.scratch_stride = tail;
         if (std::getenv("QLB_DEBUG"))
-            std::fprintf(stderr, "[qlb] decode_resident_f64_kernel: %u of %d slots in shared memory (%zu B), %zu B tail scratch per CTA, grid=%lld\n",
-                         smem_slots, args.code.slots, smem, tail, grid);
+            std::fprintf(stderr, "[qlb] decode_resident_f64_kernel: %d threads, %u of %d slots in shared memory (%zu B), %zu B tail scratch per CTA, grid=%lld\n",
+                         kThreads, smem_slots, args.code.slots, smem, tail, grid);
         QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;

@@ -2,6 +2,7 @@
 #include <algorithm>
 using namespace qlb;
 #include "qlb_stream_f32.cuh"
+#include "qlb_stream_split.cuh"
 
 namespace
 {
@@ -34,9 +35,96 @@ namespace
         return QLB_OK;
     }
 
+    // The phase-split form (qlb_stream_split.cuh): one kernel per pass over all groups, in waves when device memory cannot
+    // hold the message arrays of every group at once. Nothing here waits for the device.
+    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    int launch_stream_split(qlb_ctx *ctx, DecodeArgs &args, size_t budget)
+    {
+        const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
+        // groups per bundle: 2 KB of contiguous memory per slot when there are enough groups (see qlb_stream_split.cuh)
+        int B = VEC == 4 ? 4 : 1;
+        if (const char *e = std::getenv("QLB_SPLIT_BUNDLE"))
+            B = std::atoi(e);
+        while (B > 1 && groups < B)
+            B /= 2;
+        if (B != 1 && B != 2 && B != 4 && B != 8)
+            B = 1;
+        const size_t per_bundle = split_bundle_bytes(args.code.n, args.code.m, args.code.slots, VEC, B);
+        const long long fit_bundles = (long long)(budget / per_bundle);
+        if (fit_bundles < 1)
+            return fail(QLB_ERR_UNSUPPORTED, "streaming decoder: device memory cannot hold the messages of one bundle of frame groups");
+        const long long bundles = (groups + B - 1) / B;
+        const long long waves = (bundles + fit_bundles - 1) / fit_bundles;
+        const long long bundles_per_wave = (bundles + waves - 1) / waves; // equal waves instead of full ones and a remainder
+        const long long per_wave = bundles_per_wave * B;                  // groups
+        const size_t state_words = (size_t)per_wave * 12 + (size_t)bundles_per_wave + 16;
+        QLB_CUDA(ctx->scratch.reserve((size_t)bundles_per_wave * per_bundle + state_words * 4));
+        SplitState st{};
+        st.bundles = static_cast<unsigned char *>(ctx->scratch.p);
+        st.bundle_stride = per_bundle;
+        st.bundle = B;
+        uint32_t *words = reinterpret_cast<uint32_t *>(st.bundles + (size_t)bundles_per_wave * per_bundle);
+        st.act = words;
+        st.bad = words + 4 * per_wave;
+        st.succ = words + 8 * per_wave;
+        st.list = words + 12 * per_wave;
+        st.n_live = st.list + bundles_per_wave;
+        if (args.syndrome_out)
+            QLB_CUDA(cudaMemsetAsync(args.syndrome_out, 0, (size_t)args.n_frames * args.code.words_m * 4, ctx->stream));
+        args.queue = ctx->d_counters;
+        args.iter_total = ctx->d_counters + 1;
+
+        auto k_setup = stream_setup_kernel<Rule, kReconcile, kBW, VEC>;
+        auto k_check = stream_check_kernel<Rule, kReconcile, VEC>;
+        auto k_update = stream_update_kernel<VEC>;
+        auto k_bit = stream_bit_kernel<Rule, kReconcile, kBW, VEC>;
+        auto k_final = stream_finalize_kernel<kReconcile, VEC>;
+        int occ_check = 1, occ_bit = 1;
+        QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_check, k_check, kSplitCheckThreads, 0));
+        QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bit, k_bit, kSplitBitThreads, 0));
+        if (const char *e = std::getenv("QLB_SPLIT_OCC")) // experiments: "check,bit" resident CTAs per SM
+        {
+            int a = 0, b = 0;
+            if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0)
+                occ_check = std::min(occ_check, a), occ_bit = std::min(occ_bit, b);
+        }
+        const unsigned grid_check = (unsigned)(ctx->sm_count * std::max(1, occ_check)), grid_bit = (unsigned)(ctx->sm_count * std::max(1, occ_bit));
+        if (std::getenv("QLB_DEBUG"))
+            std::fprintf(stderr, "[qlb] stream split VEC=%d: %lld groups of %lld frames, bundles of %d, %lld wave(s) of <= %lld groups, %zu B per bundle; check grid %u (%d/SM), bit grid %u (%d/SM)\n",
+                         VEC, groups, G, B, waves, per_wave, per_bundle, grid_check, occ_check, grid_bit, occ_bit);
+        for (long long w = 0; w < waves; ++w)
+        {
+            st.group0 = w * per_wave;
+            st.n_groups = (int)std::min<long long>(per_wave, groups - st.group0);
+            if (st.n_groups <= 0)
+                break;
+            const unsigned grid_groups = (unsigned)std::min<long long>(st.n_groups, 2LL * ctx->sm_count);
+            k_setup<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st);
+            for (int it = 0;; ++it)
+            {
+                k_check<<<grid_check, kSplitCheckThreads, 0, ctx->stream>>>(args, st, it);
+                k_update<<<1, 1024, 0, ctx->stream>>>(args, st, it);
+                if (it == args.max_it)
+                    break;
+                k_bit<<<grid_bit, kSplitBitThreads, 0, ctx->stream>>>(args, st);
+            }
+            k_final<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st);
+            QLB_CUDA(cudaGetLastError());
+            ctx->launches += 2 + 3ULL * (unsigned)args.max_it + 2;
+        }
+        return QLB_OK;
+    }
+
     template <typename Rule, bool kReconcile>
     int launch_stream_bw(qlb_ctx *ctx, DecodeArgs &args)
     {
+        if (!std::getenv("QLB_STREAM_PERSISTENT") && args.code.uniform_bit_w == 3)
+        {
+            size_t free_b = 0, total_b = 0;
+            QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t budget = (free_b + ctx->scratch.cap) / 20 * 17;
+            return args.n_frames > 32 ? launch_stream_split<Rule, kReconcile, 3, 4>(ctx, args, budget) : launch_stream_split<Rule, kReconcile, 3, 1>(ctx, args, budget);
+        }
         // 128-bit accesses (128 frames per group) unless the per-SM message arrays would not fit in device memory
         size_t free_b = 0, total_b = 0;
         QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));

@@ -79,6 +79,8 @@ config_data get_config_data(fs::path config_path)
         }
         if (root.contains("device_fp32_fast_math"))
             cfg.DEVICE_FP32_FAST = root.at("device_fp32_fast_math").as_bool();
+        if (root.contains("device_fp64_fused_ratio"))
+            cfg.DEVICE_FP64_FUSED = root.at("device_fp64_fused_ratio").as_bool();
         if (root.contains("device_gpus"))
             cfg.DEVICE_GPUS = static_cast<int>(root.at("device_gpus").as_size());
         if (root.contains("device_generate_keys"))

@@ -119,6 +119,8 @@ namespace qkd_b200
         p.enable_threshold = CFG.ENABLE_SUM_PRODUCT_MSG_LLR_THRESHOLD ? 1 : 0; // read inside the reference's decoder (:246,313)
         p.threshold = threshold;
         p.flags = (p.precision == QLB_PRECISION_F32 && CFG.DEVICE_FP32_FAST) ? QLB_FLAG_F32_FAST_MATH : 0;
+        if (p.precision == QLB_PRECISION_F64 && CFG.DEVICE_FP64_FUSED)
+            p.flags |= QLB_FLAG_F64_FUSED_RATIO;
         return p;
     }
 

@@ -19,15 +19,15 @@ for q in qs:
     res = torch.zeros(frames, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     for v in variants:
-        p = capi.make_params(64 if v == "f64" else 32, 100, 100.0, True, fast_math=(v == "f32fast"))
-        nf = frames if v != "f64" else max(frames // 4, 148)
+        p = capi.make_params(64 if v.startswith("f64") else 32, 100, 100.0, True, fast_math=v in ("f32fast", "f64fused"))
+        nf = frames if not v.startswith("f64") else max(frames // 4, 148)
         for rep in range(2):
             ctx.timer_start()
             ctx.reconcile_device(code, p, nf, a.data_ptr(), b.data_ptr(), lp.data_ptr(), it.data_ptr(), res.data_ptr())
             ms = ctx.timer_stop()
         iters = int(it[:nf].sum().item()); ok = int((res[:nf] & 1).sum().item()); km = int(((res[:nf] >> 1) & 1).sum().item())
         fi = iters / (ms * 1e-3)
-        bytes_per = 16 if v != "f64" else 32
+        bytes_per = 16 if not v.startswith("f64") else 32
         print(f"q={q:.3f} {v:8s} frames={nf} ms={ms:9.3f} frames/s={nf/(ms*1e-3):12.1f} mean_it={iters/nf:6.2f} "
               f"frame-it/s={fi/1e6:8.3f}M  alg GB/s={fi*mat.e*bytes_per/1e9:9.1f} ({fi*mat.e*bytes_per/6537.3e9:.3f} of HBM peak) ok={ok} keys={km}",
               flush=True)

@@ -63,10 +63,16 @@ def test_large_block_length_matches_oracle(ctx, oracle):
                 assert (capi.unpack_bits(dec, n) == wdec).all()
 
 
-def test_streaming_kernel_equals_resident_kernel(ctx, oracle):
-    """The frame-interleaved HBM-streaming kernel (forced with the tier-3 test hook) runs the same node arithmetic as the
+@pytest.mark.parametrize("form", ["split", "persistent"])
+def test_streaming_kernel_equals_resident_kernel(ctx, oracle, form, monkeypatch):
+    """The frame-interleaved HBM-streaming decoder (forced with the tier-3 test hook) runs the same node arithmetic as the
     SM-resident kernel: iterations, flags and decoded keys must be identical, for a ragged batch (300 frames = 2 groups + 44)
-    mixing QBER points, in both fp32 rules."""
+    mixing QBER points, in both fp32 rules. Both forms: one kernel per pass over all groups (the default) and the persistent
+    one-CTA-per-group kernel (QLB_STREAM_PERSISTENT, read by the library at launch time)."""
+    if form == "persistent":
+        monkeypatch.setenv("QLB_STREAM_PERSISTENT", "1")
+    else:
+        monkeypatch.delenv("QLB_STREAM_PERSISTENT", raising=False)
     mat = codes.load_npz(codes.NORTH_STAR)
     code = capi.Code.from_graph(mat)
     seeds = oracle.trial_seeds(31337, 300)
@@ -89,6 +95,10 @@ def test_streaming_kernel_equals_resident_kernel(ctx, oracle):
     it_r, res_r, bits_r = ctx.sum_product(code, capi.make_params(32, 60, 100.0, True, fast_math=True), llr, syn)
     it_s, res_s, bits_s = ctx.sum_product(code, capi.make_params(32, 60, 100.0, True, fast_math=True, tier=3), llr, syn)
     assert (it_r == it_s).all() and (res_r == res_s).all() and (bits_r == bits_s).all()
+    # a batch of <= 32 frames takes the 32-frame-group instantiation
+    r = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=True), A[:21], B[:21], Q[:21], want_syndrome=True)
+    s = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=True, tier=3), A[:21], B[:21], Q[:21], want_syndrome=True)
+    assert all((x == y).all() for x, y in zip(r, s))
 
 
 def test_streaming_kernel_large_block_length(ctx, oracle):
