@@ -166,11 +166,25 @@ def materialize() -> dict:
     return out
 
 
+def save_npz(mat: Matrix, name: str) -> Path:
+    """Writes a matrix in the format load_npz reads (data/codes/<name>.npz)."""
+    idx_t = np.uint16 if max(mat.n, mat.m) < 65536 else np.uint32
+    p = CODES / f"{name}.npz"
+    np.savez_compressed(p, n=mat.n, m=mat.m, is_regular=mat.is_regular, max_bit_w=mat.max_bit_w, max_check_w=mat.max_check_w,
+                        check_w=np.diff(mat.row_ptr).astype(np.uint8), col_idx=mat.col_idx.astype(idx_t),
+                        bit_w=np.diff(mat.col_ptr).astype(np.uint8), row_idx=mat.row_idx.astype(idx_t), source=mat.name, dense=False)
+    return p
+
+
 def peg_code(n: int, m: int, dv: int = 3, seed: int = 666, bfs_limit: int = 4096) -> Matrix:
     """A seeded PEG code of column weight `dv` (host/peg.cpp), cached as alist under data/_generated/peg/ -- the
-    construction the shipped N=10240 code is consistent with; used for BASELINE.json configs[3] and configs[4]."""
+    construction the shipped N=10240 code is consistent with; used for BASELINE.json configs[3] and configs[4].
+    A committed copy data/codes/peg_n<n>_m<m>_cw<dv>_seed<seed>_bfs<limit>.npz (the generator's own output) is used when present."""
     import subprocess
     from . import build
+    cached = CODES / f"peg_n{n}_m{m}_cw{dv}_seed{seed}_bfs{bfs_limit}.npz"
+    if cached.exists():
+        return load_npz(cached)
     rate = 1.0 - m / n
     path = GENERATED / "peg" / f"(N={n},M={m},R={rate:.2f},CW={dv},SEED={seed}).txt"
     if not path.exists():

@@ -2,7 +2,7 @@
 // decisions bit-transposed per group), same node arithmetic (stream_check, the resident kernel's rules), but every pass of
 // the flooding schedule is its own kernel over ALL groups of the launch:
 //
-//     setup | check(0) update(0) bit | check(1) update(1) bit | ... | check(max_it) update(max_it) | finalize
+//     setup init | check(0) update(0) bit | check(1) update(1) bit | ... | check(max_it) update(max_it) | finalize
 //
 // Why: the persistent one-CTA-per-group kernel ties a group to one SM for its whole life -- it needs as many groups as SMs
 // (N = 1 000 000: HBM holds 99 groups, so 49 SMs idle), the last groups of a launch run on a mostly empty chip, and one
@@ -118,26 +118,17 @@ namespace qlb
         return ns;
     }
 
-    // ---- set-up: transposed keys, priors into the messages, frame bookkeeping; one CTA per group at a time -------------------
-    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    // ---- set-up, part 1: transposed keys / syndromes and frame bookkeeping; one CTA per group at a time --------------------------
+    template <bool kReconcile, int VEC>
     __global__ void __launch_bounds__(kSplitSetupThreads) stream_setup_kernel(const DecodeArgs args, const SplitState st)
     {
         constexpr int G = 32 * VEC;
-        constexpr int kWarps = kSplitSetupThreads / 32;
         const CodeDev &code = args.code;
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-        const float unit = Rule::kUnit;
         for (uint32_t g = blockIdx.x; g < (uint32_t)st.n_groups; g += gridDim.x)
         {
             const SplitGroup sg = split_group(st, code, VEC, g);
             const long long f0 = (st.group0 + g) * G;
-            float lp[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j)
-            {
-                const long long f = f0 + (long long)VEC * lane + j;
-                lp[j] = (kReconcile && f < args.n_frames) ? unit * (float)args.log_prior[f] : 0.f;
-            }
             if (kReconcile)
             {
                 transpose_in<VEC>(args.bob, f0, args.n_frames, code.words_n, n, sg.bobT);
@@ -152,8 +143,63 @@ namespace qlb
                     for (int j = 0; j < VEC; ++j)
                         sg.synT[(size_t)p * VEC + j] = sg.aliceT[(size_t)code.check_order[p] * VEC + j];
             }
+            if (warp == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    const long long f = f0 + (long long)VEC * lane + j;
+                    const bool live = f < args.n_frames;
+                    if (live)
+                        args.iterations[f] = (uint32_t)args.max_it;
+                    const uint32_t word = __ballot_sync(0xffffffffu, live);
+                    if (lane == 0)
+                    {
+                        st.act[g * 4 + j] = word;
+                        st.bad[g * 4 + j] = 0;
+                        st.succ[g * 4 + j] = 0;
+                    }
+                }
+                if (lane == 0 && g % (uint32_t)st.bundle == 0)
+                    st.list[g / (uint32_t)st.bundle] = g / (uint32_t)st.bundle;
+            }
             __syncthreads();
-            for (int i = warp; i < n; i += kWarps)
+        }
+        if (blockIdx.x == 0 && tid == 0)
+            *st.n_live = (uint32_t)((st.n_groups + st.bundle - 1) / st.bundle);
+    }
+
+    // ---- set-up, part 2: messages <- priors (src/qkd_ldpc_algorithm.cpp:182-190), Alice's bit riding in bit 0 (reconcile mode) so
+    // that the first check pass yields her syndrome; decisions <- 0. Same work split as the bit pass: (bundle, chunk of bits),
+    // adjacent warps on the B groups of the bundle, so the scattered rows are written in 2 KB units.
+    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    __global__ void __launch_bounds__(kSplitBitThreads) stream_init_kernel(const DecodeArgs args, const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        constexpr int kWarps = kSplitBitThreads / 32;
+        const CodeDev &code = args.code;
+        const int n = code.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const float unit = Rule::kUnit;
+        const int B = st.bundle, step = kWarps / B;
+        const uint32_t n_bundles = (uint32_t)((st.n_groups + B - 1) / B);
+        const uint32_t chunks = ((uint32_t)n + kSplitBitChunk - 1) / kSplitBitChunk;
+        const unsigned long long items = (unsigned long long)n_bundles * chunks;
+        for (unsigned long long item = blockIdx.x; item < items; item += gridDim.x)
+        {
+            const uint32_t g = (uint32_t)(item / chunks) * (uint32_t)B + (uint32_t)(warp % B);
+            const int i0 = (int)(item % chunks) * kSplitBitChunk, i1 = min(n, i0 + kSplitBitChunk);
+            if (g >= (uint32_t)st.n_groups)
+                continue;
+            const SplitGroup sg = split_group(st, code, VEC, g);
+            const long long f0 = (st.group0 + g) * G;
+            float lp[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                const long long f = f0 + (long long)VEC * lane + j;
+                lp[j] = (kReconcile && f < args.n_frames) ? unit * (float)args.log_prior[f] : 0.f;
+            }
+            for (int i = i0 + warp / B; i < i1; i += step)
             {
                 float pv[VEC];
 #pragma unroll
@@ -182,30 +228,7 @@ namespace qlb
                     for (int j = 0; j < VEC; ++j)
                         sg.zT[(size_t)i * VEC + j] = 0;
             }
-            if (warp == 0)
-            {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                {
-                    const long long f = f0 + (long long)VEC * lane + j;
-                    const bool live = f < args.n_frames;
-                    if (live)
-                        args.iterations[f] = (uint32_t)args.max_it;
-                    const uint32_t word = __ballot_sync(0xffffffffu, live);
-                    if (lane == 0)
-                    {
-                        st.act[g * 4 + j] = word;
-                        st.bad[g * 4 + j] = 0;
-                        st.succ[g * 4 + j] = 0;
-                    }
-                }
-                if (lane == 0 && g % (uint32_t)st.bundle == 0)
-                    st.list[g / (uint32_t)st.bundle] = g / (uint32_t)st.bundle;
-            }
-            __syncthreads();
         }
-        if (blockIdx.x == 0 && tid == 0)
-            *st.n_live = (uint32_t)((st.n_groups + st.bundle - 1) / st.bundle);
     }
 
     // ---- check pass over the live bundles: work item = (bundle, kSplitCheckChunk consecutive sorted checks) -------------------

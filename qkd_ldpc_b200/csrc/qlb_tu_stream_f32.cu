@@ -74,7 +74,8 @@ namespace
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;
 
-        auto k_setup = stream_setup_kernel<Rule, kReconcile, kBW, VEC>;
+        auto k_setup = stream_setup_kernel<kReconcile, VEC>;
+        auto k_init = stream_init_kernel<Rule, kReconcile, kBW, VEC>;
         auto k_check = stream_check_kernel<Rule, kReconcile, VEC>;
         auto k_update = stream_update_kernel<VEC>;
         auto k_bit = stream_bit_kernel<Rule, kReconcile, kBW, VEC>;
@@ -100,6 +101,7 @@ namespace
                 break;
             const unsigned grid_groups = (unsigned)std::min<long long>(st.n_groups, 2LL * ctx->sm_count);
             k_setup<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st);
+            k_init<<<grid_bit, kSplitBitThreads, 0, ctx->stream>>>(args, st);
             for (int it = 0;; ++it)
             {
                 k_check<<<grid_check, kSplitCheckThreads, 0, ctx->stream>>>(args, st, it);
@@ -110,7 +112,7 @@ namespace
             }
             k_final<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st);
             QLB_CUDA(cudaGetLastError());
-            ctx->launches += 2 + 3ULL * (unsigned)args.max_it + 2;
+            ctx->launches += 3 + 3ULL * (unsigned)args.max_it + 2;
         }
         return QLB_OK;
     }
