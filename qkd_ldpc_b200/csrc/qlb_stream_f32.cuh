@@ -199,8 +199,11 @@ namespace qlb
                 T[(size_t)bit * VEC + j] = mine;
         }
     }
+    // fmap_g (optional): frame index of each of the group's 32 * VEC columns (0xFFFFFFFF = none) instead of f0 + column;
+    // keep[j] (with fmap_g): only the columns whose bit is set in keep[j] are written
     template <int VEC>
-    __device__ __forceinline__ void transpose_out(const uint32_t *__restrict__ T, long long f0, long long n_frames, int words, int n, uint32_t *__restrict__ frames)
+    __device__ __forceinline__ void transpose_out(const uint32_t *__restrict__ T, long long f0, long long n_frames, int words, int n, uint32_t *__restrict__ frames,
+                                                  const uint32_t *__restrict__ fmap_g = nullptr, const uint32_t *keep = nullptr)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for (int item = warp; item < words * VEC; item += nwarps)
@@ -216,7 +219,12 @@ namespace qlb
                 if (lane == l)
                     mine = row;
             }
-            const long long f = f0 + (long long)VEC * lane + j;
+            long long f = f0 + (long long)VEC * lane + j;
+            if (fmap_g)
+            {
+                const uint32_t fm = fmap_g[VEC * lane + j];
+                f = (fm == 0xFFFFFFFFu || (keep && !((keep[j] >> lane) & 1u))) ? n_frames : (long long)fm;
+            }
             if (f < n_frames)
                 frames[f * words + wd] = mine;
         }

@@ -51,10 +51,17 @@ namespace qlb
         uint32_t *succ; // [n_groups][4] frames whose decisions satisfied the syndrome
         uint32_t *list; // [n_bundles] bundles with a live group, [0, *n_live)
         uint32_t *n_live;
-        long long group0; // index of this wave's first group in the whole batch (frame = (group0 + g) * G + ...)
+        long long group0; // index of this wave's first group in the whole batch (initially frame = (group0 + g) * G + column)
         int n_groups;
         int bundle; // B: groups per bundle (1, 2, 4 or 8; divides the warps per CTA of the pass kernels)
+        // frame-granular compaction (stream_repack_* kernels)
+        uint32_t *fmap;     // [n_groups][G] frame index held by each column (kNoFrame: none); column = VEC * lane + j
+        uint32_t *src_of;   // [n_groups][G] repack plan: old column id (g * G + column) that moves to new column id k
+        uint32_t *fmap_new; // [n_groups][G]
+        uint32_t *repack;   // [0] repack decided, [1] live frames, [2] groups after the repack
     };
+    constexpr uint32_t kNoFrame = 0xFFFFFFFFu;
+    constexpr int kMaxRepackGroups = 256; // per wave: the bit-array move stages one word per group and frame word in shared memory
 
     // per-group arrays other than the messages (bytes)
     struct SplitSmall
@@ -152,6 +159,7 @@ namespace qlb
                     const bool live = f < args.n_frames;
                     if (live)
                         args.iterations[f] = (uint32_t)args.max_it;
+                    st.fmap[(size_t)g * G + VEC * lane + j] = live ? (uint32_t)f : kNoFrame;
                     const uint32_t word = __ballot_sync(0xffffffffu, live);
                     if (lane == 0)
                     {
@@ -349,7 +357,7 @@ namespace qlb
                         {
                             const int l = __ffs(done) - 1;
                             done &= done - 1;
-                            args.iterations[(st.group0 + g) * G + (long long)VEC * l + j] = (uint32_t)it;
+                            args.iterations[st.fmap[(size_t)g * G + VEC * l + j]] = (uint32_t)it;
                         }
                     }
                 }
@@ -365,9 +373,10 @@ namespace qlb
     }
 
     // ---- bit pass over the live bundles: work item = (bundle, kSplitBitChunk consecutive bits), U bits per warp in flight -----------
+    // fr[j]: frame index held by this lane's column j (kNoFrame: none)
     template <bool kReconcile, int kBW, int VEC, int U>
     __device__ __forceinline__ void split_bits(const DecodeArgs &args, const SplitGroup &sg, const int (&bit)[U], int lane, const float (&lp)[VEC],
-                                               const uint32_t (&act_word)[VEC], long long f0, float unit, float cap, bool clamp_b2c)
+                                               const uint32_t (&act_word)[VEC], const uint32_t (&fr)[VEC], float unit, float cap, bool clamp_b2c)
     {
         const CodeDev &code = args.code;
         const int n = code.n;
@@ -396,10 +405,7 @@ namespace qlb
                 if (kReconcile)
                     prior = __uint_as_float(__float_as_uint(lp[j]) ^ (((sg.bobT[(size_t)i * VEC + j] >> lane) & 1u) << 31));
                 else
-                {
-                    const long long f = f0 + (long long)VEC * lane + j;
-                    prior = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
-                }
+                    prior = fr[j] != kNoFrame ? unit * (float)args.llr[(size_t)fr[j] * n + i] : 0.f;
                 float t = prior;
 #pragma unroll
                 for (int a = 0; a < kBW; ++a)
@@ -457,14 +463,13 @@ namespace qlb
             if (g >= (uint32_t)st.n_groups)
                 continue;
             const SplitGroup sg = split_group(st, code, VEC, g);
-            const long long f0 = (st.group0 + g) * G;
             float lp[VEC];
-            uint32_t act_word[VEC], alive = 0;
+            uint32_t act_word[VEC], fr[VEC], alive = 0;
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
             {
-                const long long f = f0 + (long long)VEC * lane + j;
-                lp[j] = (kReconcile && f < args.n_frames) ? unit * (float)args.log_prior[f] : 0.f;
+                fr[j] = st.fmap[(size_t)g * G + VEC * lane + j];
+                lp[j] = (kReconcile && fr[j] != kNoFrame) ? unit * (float)args.log_prior[fr[j]] : 0.f;
                 act_word[j] = st.act[g * 4 + j];
                 alive |= act_word[j];
             }
@@ -479,30 +484,44 @@ namespace qlb
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     many[u] = i + u * step;
-                split_bits<kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, f0, unit, cap, clamp_b2c);
+                split_bits<kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, fr, unit, cap, clamp_b2c);
             }
 #pragma unroll 1
             for (; i < i1; i += step)
             {
                 const int one[1] = {i};
-                split_bits<kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, f0, unit, cap, clamp_b2c);
+                split_bits<kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, fr, unit, cap, clamp_b2c);
             }
         }
     }
 
     // ---- results: flags, key comparison, decoded keys and syndromes back in frame-major order; one CTA per group at a time ----
+    // only_done: called from a repack (and only when one was decided): the frames that have finished -- about to lose their
+    // columns -- get their results now; the final call handles whatever the map still holds.
     template <bool kReconcile, int VEC>
-    __global__ void __launch_bounds__(kSplitSetupThreads) stream_finalize_kernel(const DecodeArgs args, const SplitState st)
+    __global__ void __launch_bounds__(kSplitSetupThreads) stream_finalize_kernel(const DecodeArgs args, const SplitState st, int only_done)
     {
         constexpr int G = 32 * VEC;
         constexpr int kWarps = kSplitSetupThreads / 32;
         __shared__ uint32_t s_flags[kWarps][4];
+        if (only_done && !st.repack[0])
+            return;
         const CodeDev &code = args.code;
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         for (uint32_t g = blockIdx.x; g < (uint32_t)st.n_groups; g += gridDim.x)
         {
             const SplitGroup sg = split_group(st, code, VEC, g);
-            const long long f0 = (st.group0 + g) * G;
+            const uint32_t *fmap_g = st.fmap + (size_t)g * G;
+            uint32_t keep[VEC], fr[VEC], any = 0; // keep[j] bit l: column (l, j) holds a frame this call reports
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                fr[j] = fmap_g[VEC * lane + j];
+                keep[j] = __ballot_sync(0xffffffffu, fr[j] != kNoFrame) & (only_done ? ~st.act[g * 4 + j] : 0xFFFFFFFFu);
+                any |= keep[j];
+            }
+            if (!any)
+                continue;
             uint32_t differs = 0;
             if (kReconcile)
             {
@@ -539,17 +558,14 @@ namespace qlb
                 unsigned long long it_sum = 0;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                {
-                    const long long f = f0 + (long long)VEC * lane + j;
-                    if (f < args.n_frames)
+                    if ((keep[j] >> lane) & 1u)
                     {
                         uint8_t r = (st.succ[g * 4 + j] >> lane) & 1u ? 1 : 0;
                         if (kReconcile && !((differs >> j) & 1u))
                             r |= 2;
-                        args.result[f] = r;
-                        it_sum += args.iterations[f];
+                        args.result[fr[j]] = r;
+                        it_sum += args.iterations[fr[j]];
                     }
-                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
                     it_sum += __shfl_xor_sync(0xffffffffu, it_sum, o);
@@ -557,20 +573,200 @@ namespace qlb
                     atomicAdd(args.iter_total, it_sum);
             }
             if (args.decoded)
-                transpose_out<VEC>(sg.zT, f0, args.n_frames, code.words_n, n, args.decoded);
+                transpose_out<VEC>(sg.zT, 0, args.n_frames, code.words_n, n, args.decoded, fmap_g, keep);
             if (kReconcile && args.syndrome_out)
                 for (int p = warp; p < m; p += kWarps)
                 {
                     const uint32_t jn = code.check_order[p];
 #pragma unroll
                     for (int j = 0; j < VEC; ++j)
-                    {
-                        const long long f = f0 + (long long)VEC * lane + j;
-                        if (f < args.n_frames && ((sg.synT[(size_t)p * VEC + j] >> lane) & 1u))
-                            atomicOr(&args.syndrome_out[f * code.words_m + (jn >> 5)], 1u << (jn & 31));
-                    }
+                        if (((keep[j] >> lane) & 1u) && ((sg.synT[(size_t)p * VEC + j] >> lane) & 1u))
+                            atomicOr(&args.syndrome_out[(size_t)fr[j] * code.words_m + (jn >> 5)], 1u << (jn & 31));
                 }
             __syncthreads();
         }
+    }
+
+    // =============================================================================================================================
+    // Frame-granular compaction. At a waterfall QBER most frames of a group converge early while a few run to max_it; their
+    // columns would keep streaming. A repack (attempted at a few fixed rounds, decided on the device) moves the columns of the
+    // live frames of ALL groups to the front -- new column k = rank of the frame among the live ones in (group, column)
+    // order -- so that the passes touch ceil(live / G) groups from then on. Per-frame inputs and outputs are reached through
+    // `fmap`. All moves are in place: a live column never moves to a later position, so for one message row set (one slot)
+    // or one node's bit words, reading every source before writing any destination is enough.
+    //   plan -> finalize(only_done) -> move_msg -> move_bits -> commit      (each returns at once when no repack was decided)
+    // =============================================================================================================================
+    template <int VEC>
+    __global__ void __launch_bounds__(1024) stream_repack_plan_kernel(const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        __shared__ uint32_t s_cnt[kMaxRepackGroups + 1];
+        __shared__ uint32_t s_live_groups;
+        const int tid = threadIdx.x, ng = st.n_groups;
+        if (tid == 0)
+        {
+            st.repack[0] = 0;
+            s_live_groups = 0;
+        }
+        if (*st.n_live == 0 || ng > kMaxRepackGroups || ng < 2)
+            return;
+        __syncthreads();
+        uint32_t cnt = 0;
+        if (tid < ng)
+        {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                cnt += __popc(st.act[tid * 4 + j]);
+            s_cnt[tid] = cnt;
+            if (cnt)
+                atomicAdd(&s_live_groups, 1u);
+        }
+        __syncthreads();
+        if (tid == 0) // exclusive scan over <= 256 groups
+        {
+            uint32_t run = 0;
+            for (int g = 0; g < ng; ++g)
+            {
+                const uint32_t c = s_cnt[g];
+                s_cnt[g] = run;
+                run += c;
+            }
+            s_cnt[ng] = run;
+        }
+        __syncthreads();
+        const uint32_t live = s_cnt[ng], new_groups = (live + G - 1) / G;
+        // worth it when at most half of the streamed columns are live and at least one group disappears
+        const bool go = live > 0 && 2u * live <= s_live_groups * (uint32_t)G && new_groups < s_live_groups;
+        if (!go)
+            return;
+        if (tid < ng)
+        {
+            uint32_t k = s_cnt[tid];
+            for (int c = 0; c < G; ++c)
+                if ((st.act[tid * 4 + c % VEC] >> (c / VEC)) & 1u)
+                {
+                    st.src_of[k] = (uint32_t)tid * G + c;
+                    st.fmap_new[k] = st.fmap[(size_t)tid * G + c];
+                    ++k;
+                }
+        }
+        for (uint32_t k = live + tid; k < (uint32_t)ng * G; k += blockDim.x)
+        {
+            st.src_of[k] = kNoFrame;
+            st.fmap_new[k] = kNoFrame;
+        }
+        if (tid == 0)
+        {
+            st.repack[1] = live;
+            st.repack[2] = new_groups;
+            __threadfence();
+            st.repack[0] = 1;
+        }
+    }
+
+    // message columns: one CTA owns a slot at a time (all groups of the wave), staging <= kRepackStage values between the reads
+    // and the writes
+    constexpr int kRepackStage = 4096, kRepackThreads = 256;
+    template <int VEC>
+    __global__ void __launch_bounds__(kRepackThreads) stream_repack_msg_kernel(const DecodeArgs args, const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        __shared__ float s_val[kRepackStage];
+        if (!st.repack[0])
+            return;
+        const uint32_t live = st.repack[1];
+        const int B = st.bundle;
+        const size_t rs = (size_t)B * G;
+        const int slots = args.code.slots;
+        auto at = [&](uint32_t slot, uint32_t col_id) -> float *
+        {
+            const uint32_t g = col_id / G, c = col_id % G;
+            return reinterpret_cast<float *>(st.bundles + (size_t)(g / B) * st.bundle_stride) + ((size_t)slot * rs + (size_t)(g % B) * G + c);
+        };
+        for (uint32_t slot = blockIdx.x; slot < (uint32_t)slots; slot += gridDim.x)
+            for (uint32_t k0 = 0; k0 < live; k0 += kRepackStage)
+            {
+                const uint32_t k1 = min(live, k0 + kRepackStage);
+                for (uint32_t k = k0 + threadIdx.x; k < k1; k += kRepackThreads)
+                    s_val[k - k0] = *at(slot, st.src_of[k]);
+                __syncthreads();
+                for (uint32_t k = k0 + threadIdx.x; k < k1; k += kRepackThreads)
+                    *at(slot, k) = s_val[k - k0];
+                __syncthreads();
+            }
+    }
+
+    // bit-transposed words (Bob, Alice, decisions: per bit; syndromes: per check): one warp owns a node of one array at a time
+    template <int VEC>
+    __global__ void __launch_bounds__(kRepackThreads) stream_repack_bits_kernel(const DecodeArgs args, const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        constexpr int kWarps = kRepackThreads / 32;
+        __shared__ uint32_t s_old[kWarps][kMaxRepackGroups * VEC];
+        if (!st.repack[0])
+            return;
+        const CodeDev &code = args.code;
+        const int n = code.n, m = code.m, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ng = st.n_groups;
+        const uint32_t new_groups = st.repack[2];
+        const SplitSmall cv = split_small_carve(n, m, VEC);
+        const int B = st.bundle;
+        const size_t small0 = align_up((size_t)code.slots * B * G * 4, 256);
+        const unsigned long long nodes = 3ull * n + m;
+        for (unsigned long long q = (unsigned long long)blockIdx.x * kWarps + warp; q < nodes; q += (unsigned long long)gridDim.x * kWarps)
+        {
+            const int which = q < 3ull * n ? (int)(q / n) : 3;
+            const size_t node = which < 3 ? (size_t)(q % n) : (size_t)(q - 3ull * n);
+            const size_t off = (which == 0 ? cv.bobT : which == 1 ? cv.aliceT : which == 2 ? cv.zT : cv.synT) + node * VEC * 4;
+            auto words_of = [&](uint32_t g) -> uint32_t *
+            { return reinterpret_cast<uint32_t *>(st.bundles + (size_t)(g / B) * st.bundle_stride + small0 + (size_t)(g % B) * cv.total + off); };
+            for (int x = lane; x < ng * VEC; x += 32)
+                s_old[warp][x] = words_of((uint32_t)(x / VEC))[x % VEC];
+            __syncwarp();
+            for (uint32_t gn = 0; gn < new_groups; ++gn)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    const uint32_t old = st.src_of[(size_t)gn * G + VEC * lane + j];
+                    uint32_t bit = 0;
+                    if (old != kNoFrame)
+                    {
+                        const uint32_t c = old % G;
+                        bit = (s_old[warp][(old / G) * VEC + c % VEC] >> (c / VEC)) & 1u;
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0)
+                        words_of(gn)[j] = word;
+                }
+            __syncwarp();
+        }
+    }
+
+    template <int VEC>
+    __global__ void __launch_bounds__(1024) stream_repack_commit_kernel(const SplitState st)
+    {
+        constexpr int G = 32 * VEC;
+        if (!st.repack[0])
+            return;
+        const uint32_t live = st.repack[1], new_groups = st.repack[2];
+        const int tid = threadIdx.x, ng = st.n_groups, B = st.bundle;
+        for (uint32_t k = tid; k < (uint32_t)ng * G; k += blockDim.x)
+            st.fmap[k] = st.fmap_new[k];
+        for (int x = tid; x < ng * 4; x += blockDim.x)
+        {
+            const uint32_t g = x / 4, j = x % 4;
+            uint32_t word = 0;
+            if ((int)j < VEC)
+                for (int l = 0; l < 32; ++l)
+                    if (g * G + (uint32_t)(VEC * l) + j < live)
+                        word |= 1u << l;
+            st.act[x] = word;
+            st.bad[x] = 0;
+            st.succ[x] = 0;
+        }
+        const uint32_t new_bundles = (new_groups + B - 1) / B;
+        for (uint32_t b = tid; b < new_bundles; b += blockDim.x)
+            st.list[b] = b;
+        if (tid == 0)
+            *st.n_live = new_bundles;
     }
 }

@@ -57,7 +57,9 @@ namespace
         const long long waves = (bundles + fit_bundles - 1) / fit_bundles;
         const long long bundles_per_wave = (bundles + waves - 1) / waves; // equal waves instead of full ones and a remainder
         const long long per_wave = bundles_per_wave * B;                  // groups
-        const size_t state_words = (size_t)per_wave * 12 + (size_t)bundles_per_wave + 16;
+        if (args.n_frames >= 0xFFFFFFFFLL)
+            return fail(QLB_ERR_UNSUPPORTED, "streaming decoder: more than 2^32 - 2 frames in one call");
+        const size_t state_words = (size_t)per_wave * 12 + (size_t)bundles_per_wave + 16 + 3 * (size_t)per_wave * G;
         QLB_CUDA(ctx->scratch.reserve((size_t)bundles_per_wave * per_bundle + state_words * 4));
         SplitState st{};
         st.bundles = static_cast<unsigned char *>(ctx->scratch.p);
@@ -69,6 +71,10 @@ namespace
         st.succ = words + 8 * per_wave;
         st.list = words + 12 * per_wave;
         st.n_live = st.list + bundles_per_wave;
+        st.repack = st.n_live + 4;
+        st.fmap = st.n_live + 16;
+        st.src_of = st.fmap + (size_t)per_wave * G;
+        st.fmap_new = st.src_of + (size_t)per_wave * G;
         if (args.syndrome_out)
             QLB_CUDA(cudaMemsetAsync(args.syndrome_out, 0, (size_t)args.n_frames * args.code.words_m * 4, ctx->stream));
         args.queue = ctx->d_counters;
@@ -80,6 +86,13 @@ namespace
         auto k_update = stream_update_kernel<VEC>;
         auto k_bit = stream_bit_kernel<Rule, kReconcile, kBW, VEC>;
         auto k_final = stream_finalize_kernel<kReconcile, VEC>;
+        auto k_plan = stream_repack_plan_kernel<VEC>;
+        auto k_mvmsg = stream_repack_msg_kernel<VEC>;
+        auto k_mvbits = stream_repack_bits_kernel<VEC>;
+        auto k_commit = stream_repack_commit_kernel<VEC>;
+        // rounds after which a repack is attempted (decided on the device: live columns <= half of the streamed ones)
+        const bool repack_on = !std::getenv("QLB_SPLIT_NO_REPACK") && per_wave <= kMaxRepackGroups && per_wave >= 2;
+        auto repack_round = [](int it) { return it == 6 || it == 10 || it == 16 || it == 24 || it == 36 || it == 54 || it == 80; };
         int occ_check = 1, occ_bit = 1;
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_check, k_check, kSplitCheckThreads, 0));
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bit, k_bit, kSplitBitThreads, 0));
@@ -108,9 +121,18 @@ namespace
                 k_update<<<1, 1024, 0, ctx->stream>>>(args, st, it);
                 if (it == args.max_it)
                     break;
+                if (repack_on && repack_round(it))
+                {
+                    k_plan<<<1, 1024, 0, ctx->stream>>>(st);
+                    k_final<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st, 1);
+                    k_mvmsg<<<grid_bit, kRepackThreads, 0, ctx->stream>>>(args, st);
+                    k_mvbits<<<grid_bit, kRepackThreads, 0, ctx->stream>>>(args, st);
+                    k_commit<<<1, 1024, 0, ctx->stream>>>(st);
+                    ctx->launches += 5;
+                }
                 k_bit<<<grid_bit, kSplitBitThreads, 0, ctx->stream>>>(args, st);
             }
-            k_final<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st);
+            k_final<<<grid_groups, kSplitSetupThreads, 0, ctx->stream>>>(args, st, 0);
             QLB_CUDA(cudaGetLastError());
             ctx->launches += 3 + 3ULL * (unsigned)args.max_it + 2;
         }

@@ -63,16 +63,18 @@ def test_large_block_length_matches_oracle(ctx, oracle):
                 assert (capi.unpack_bits(dec, n) == wdec).all()
 
 
-@pytest.mark.parametrize("form", ["split", "persistent"])
+@pytest.mark.parametrize("form", ["split", "split_norepack", "persistent"])
 def test_streaming_kernel_equals_resident_kernel(ctx, oracle, form, monkeypatch):
     """The frame-interleaved HBM-streaming decoder (forced with the tier-3 test hook) runs the same node arithmetic as the
     SM-resident kernel: iterations, flags and decoded keys must be identical, for a ragged batch (300 frames = 2 groups + 44)
     mixing QBER points, in both fp32 rules. Both forms: one kernel per pass over all groups (the default) and the persistent
     one-CTA-per-group kernel (QLB_STREAM_PERSISTENT, read by the library at launch time)."""
+    monkeypatch.delenv("QLB_STREAM_PERSISTENT", raising=False)
+    monkeypatch.delenv("QLB_SPLIT_NO_REPACK", raising=False)
     if form == "persistent":
         monkeypatch.setenv("QLB_STREAM_PERSISTENT", "1")
-    else:
-        monkeypatch.delenv("QLB_STREAM_PERSISTENT", raising=False)
+    elif form == "split_norepack":  # without the frame-granular compaction (the mixed-QBER batch below triggers several repacks)
+        monkeypatch.setenv("QLB_SPLIT_NO_REPACK", "1")
     mat = codes.load_npz(codes.NORTH_STAR)
     code = capi.Code.from_graph(mat)
     seeds = oracle.trial_seeds(31337, 300)
