@@ -104,8 +104,8 @@ namespace qlb
             for (int k = 0; k < W; ++k)
             {
                 e[k] = ex2_approx(-fabsf(v[k]));
-                A *= 1.f - e[k];
-                B *= 1.f + e[k];
+                A = fmaf(-A, e[k], A); // A (1 - e), one rounding
+                B = fmaf(B, e[k], B);  // B (1 + e)
             }
             const float S = B + A, D = B - A;
 #pragma unroll
