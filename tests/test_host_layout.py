@@ -148,3 +148,22 @@ def test_pack_unpack_roundtrip():
         w = capi.pack_bits(b)
         assert w.shape == (3, (n + 31) // 32)
         assert (capi.unpack_bits(w, n) == b).all()
+
+
+def test_committed_peg_code_n100k_is_what_it_says():
+    """data/codes/peg_n100000_*.npz (configs[3], used by bench.py's stream_n100k variant and the N = 100 000 GPU tests) is the PEG
+    generator's own output: column weight 3 everywhere, check weights within one of each other, both adjacency halves sorted,
+    describing the same duplicate-free edge set, and accepted by qlb_code_create."""
+    from qkd_ldpc_b200 import capi, codes
+    mat = codes.peg_code(100000, 51080, 3, 666, bfs_limit=2000)
+    assert (mat.n, mat.m, mat.e) == (100000, 51080, 300000)
+    bw, cw = np.diff(mat.col_ptr), np.diff(mat.row_ptr)
+    assert (bw == 3).all() and cw.max() - cw.min() <= 1 and set(np.unique(cw)) <= {5, 6}
+    rows_of_edge = np.repeat(np.arange(mat.m), cw)          # CSR half: (check, bit)
+    cols_of_edge = np.repeat(np.arange(mat.n), bw)          # CSC half: (bit, check)
+    a = np.unique(rows_of_edge.astype(np.int64) * mat.n + mat.col_idx)
+    b = np.unique(mat.row_idx.astype(np.int64) * mat.n + cols_of_edge)
+    assert a.size == mat.e and (a == b).all()
+    assert all((np.diff(mat.col_idx[mat.row_ptr[j]:mat.row_ptr[j + 1]]) > 0).all() for j in range(0, mat.m, 997))
+    code = capi.Code.from_graph(mat)  # host-side layout only: no GPU needed
+    assert code.n == mat.n and code.m == mat.m
