@@ -205,7 +205,10 @@ namespace qlb
 
     constexpr int kResidentMaxCW = 16;
     constexpr int kBitUnroll = 1; // bits per thread in flight in the bit pass (2 measured no faster: the pass is bandwidth-, not latency-bound)
-    constexpr int kResidentThreads = 1024;
+#ifndef QLB_RESIDENT_MAX_THREADS
+#define QLB_RESIDENT_MAX_THREADS 1024
+#endif
+    constexpr int kResidentThreads = QLB_RESIDENT_MAX_THREADS; // launch bound (register budget: 64 at 1024, 80 at 768)
     constexpr size_t kResidentStaticSmem = 2 * kResidentThreads * 4 + 512; // static bookkeeping declared inside the kernel
 
     __host__ __device__ inline size_t resident_smem_bytes(int n, int m, int slots, int bw)
