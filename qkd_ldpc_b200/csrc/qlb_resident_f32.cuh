@@ -237,7 +237,7 @@ namespace qlb
                 my_bob >>= 1;
             }
             else
-                prior = unit * (float)llr_f[i];
+                prior = __fmul_rn(unit, (float)llr_f[i]); // never contracted into the sum below: every fp32 kernel forms the same prior
             uint32_t sl[kBW];
             float c[kBW];
 #pragma unroll
@@ -383,7 +383,7 @@ namespace qlb
                         prior = bb ? -lp : lp;
                     }
                     else
-                        prior = unit * (float)llr_f[i];
+                        prior = __fmul_rn(unit, (float)llr_f[i]);
                     const float pv = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
 #pragma unroll
                     for (int a = 0; a < kBW; ++a)

@@ -357,7 +357,7 @@ namespace qlb
                     else
                     {
                         const long long f = f0 + (long long)VEC * lane + j;
-                        prior = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
+                        prior = f < args.n_frames ? __fmul_rn(unit, (float)args.llr[f * n + i]) : 0.f;
                     }
                     pv[j] = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
                 }
@@ -437,7 +437,7 @@ namespace qlb
                         else
                         {
                             const long long f = f0 + (long long)VEC * lane + j;
-                            prior = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
+                            prior = f < args.n_frames ? __fmul_rn(unit, (float)args.llr[f * n + i]) : 0.f;
                         }
                         float t = prior;
 #pragma unroll

@@ -224,7 +224,7 @@ namespace qlb
                     else
                     {
                         const long long f = f0 + (long long)VEC * lane + j;
-                        prior = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
+                        prior = f < args.n_frames ? __fmul_rn(unit, (float)args.llr[f * n + i]) : 0.f;
                     }
                     pv[j] = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
                 }
@@ -405,7 +405,7 @@ namespace qlb
                 if (kReconcile)
                     prior = __uint_as_float(__float_as_uint(lp[j]) ^ (((sg.bobT[(size_t)i * VEC + j] >> lane) & 1u) << 31));
                 else
-                    prior = fr[j] != kNoFrame ? unit * (float)args.llr[(size_t)fr[j] * n + i] : 0.f;
+                    prior = fr[j] != kNoFrame ? __fmul_rn(unit, (float)args.llr[(size_t)fr[j] * n + i]) : 0.f;
                 float t = prior;
 #pragma unroll
                 for (int a = 0; a < kBW; ++a)

@@ -233,7 +233,7 @@ namespace qlb
                 else
                 {
                     const long long f = f0 + (long long)VEC * lane + j;
-                    prior[j] = f < args.n_frames ? unit * (float)args.llr[f * n + i] : 0.f;
+                    prior[j] = f < args.n_frames ? __fmul_rn(unit, (float)args.llr[f * n + i]) : 0.f;
                 }
             }
             mbar_wait(&pp.bars[pp.use_stage], (uint32_t)pp.use_phase);

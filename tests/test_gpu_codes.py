@@ -103,6 +103,41 @@ def test_streaming_kernel_equals_resident_kernel(ctx, oracle, form, monkeypatch)
     assert all((x == y).all() for x, y in zip(r, s))
 
 
+def test_streaming_compaction_many_groups(ctx, oracle):
+    """1 100 frames of the N=10240 code (9 groups = 3 bundles of 4, the last one partial and ragged) drawn by the on-device
+    reference generator at QBERs that converge at very different rounds: the streaming decoder repacks the live frames
+    several times on the way (and retires whole bundles); iterations, flags, decoded keys and syndromes must stay
+    bit-identical to the SM-resident kernel, which decodes every frame on its own."""
+    mat = codes.load_npz(codes.NORTH_STAR)
+    code = capi.Code.from_graph(mat)
+    A, B, Q = [], [], []
+    for pt, (q, cnt) in enumerate(((0.03, 300), (0.06, 250), (0.08, 250), (0.085, 200), (0.0875, 60), (0.09, 40))):
+        seeds = oracle.trial_seeds(4242 + pt, cnt)
+        a, b, ex = ctx.generate(mat.n, seeds, q)
+        A.append(a); B.append(b); Q.append(np.full(cnt, ex))
+    A, B, Q = np.concatenate(A), np.concatenate(B), np.concatenate(Q)
+    perm = np.random.default_rng(7).permutation(len(Q))  # every group holds frames of every kind
+    A, B, Q = np.ascontiguousarray(A[perm]), np.ascontiguousarray(B[perm]), Q[perm]
+    p_res = capi.make_params(32, 100, 100.0, True, fast_math=True)
+    p_str = capi.make_params(32, 100, 100.0, True, fast_math=True, tier=3)
+    r = ctx.reconcile_packed(code, p_res, A, B, Q, want_syndrome=True)
+    s = ctx.reconcile_packed(code, p_str, A, B, Q, want_syndrome=True)
+    assert (r[0] == s[0]).all(), np.flatnonzero(r[0] != s[0])[:10]
+    assert (r[1] == s[1]).all() and (r[2] == s[2]).all() and (r[3] == s[3]).all()
+    assert 0 < int((r[1] & 1).sum()) < len(Q)  # the batch really mixes converging and failing frames
+    # sum-product entry (LLRs + target syndromes, no keys) through the same repacks; the priors are products here, which every
+    # fp32 kernel rounds on their own (__fmul_rn) -- a contraction into the first sum would make the chaotic, non-converging
+    # frames end on different last decisions in different kernels
+    g = graph_of(mat)
+    k = 200
+    bob = capi.unpack_bits(B[:k], mat.n)
+    llr = np.where(bob != 0, -1.0, 1.0) * np.log((1 - Q[:k]) / Q[:k])[:, None]
+    syn = capi.unpack_bits(r[3][:k], mat.m)
+    it_r, res_r, bits_r = ctx.sum_product(code, p_res, llr, syn)
+    it_s, res_s, bits_s = ctx.sum_product(code, p_str, llr, syn)
+    assert (it_r == it_s).all() and (res_r == res_s).all() and (bits_r == bits_s).all()
+
+
 def test_streaming_kernel_large_block_length(ctx, oracle):
     """N = 100 000 in fp32 goes through the streaming kernel by default; flags must equal the fp64 oracle's."""
     n, m = 100000, 51080
