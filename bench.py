@@ -415,7 +415,7 @@ def main():
             torch.cuda.synchronize()
             pbig = capi.make_params(32, it_big, THR, True, fast_math=True)
             best = None
-            for _ in range(3):
+            for _ in range(5):
                 ctx.timer_start()
                 ctx.reconcile_device(big_code, pbig, fr, ba.data_ptr(), bb.data_ptr(), blp.data_ptr(), bit_.data_ptr(), bres.data_ptr())
                 ms = ctx.timer_stop()

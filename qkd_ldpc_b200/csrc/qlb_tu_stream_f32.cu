@@ -50,7 +50,10 @@ namespace
         if (B != 1 && B != 2 && B != 4 && B != 8)
             B = 1;
         const size_t per_bundle = split_bundle_bytes(args.code.n, args.code.m, args.code.slots, VEC, B);
-        const long long fit_bundles = (long long)(budget / per_bundle);
+        long long fit_bundles = (long long)(budget / per_bundle);
+        if (const char *e = std::getenv("QLB_SPLIT_MAX_BUNDLES")) // test hook: force several waves without filling the device memory
+            if (std::atoll(e) > 0)
+                fit_bundles = std::min<long long>(fit_bundles, std::atoll(e));
         if (fit_bundles < 1)
             return fail(QLB_ERR_UNSUPPORTED, "streaming decoder: device memory cannot hold the messages of one bundle of frame groups");
         const long long bundles = (groups + B - 1) / B;

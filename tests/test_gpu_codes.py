@@ -138,6 +138,25 @@ def test_streaming_compaction_many_groups(ctx, oracle):
     assert (it_r == it_s).all() and (res_r == res_s).all() and (bits_r == bits_s).all()
 
 
+def test_streaming_decoder_in_waves(ctx, oracle, monkeypatch):
+    """When device memory cannot hold every frame group the batch is decoded in waves (here forced: at most 2 bundles = 8 groups
+    per wave for 2 500 frames = 20 groups -> 3 waves): per-wave state is re-used, frames are addressed through the wave's
+    frame map. Must equal the resident kernel frame by frame."""
+    mat = codes.load_npz(codes.NORTH_STAR)
+    code = capi.Code.from_graph(mat)
+    A, B, Q = [], [], []
+    for pt, (q, cnt) in enumerate(((0.04, 900), (0.075, 800), (0.085, 500), (0.095, 300))):
+        a, b, ex = ctx.generate(mat.n, oracle.trial_seeds(900 + pt, cnt), q)
+        A.append(a); B.append(b); Q.append(np.full(cnt, ex))
+    A, B, Q = np.concatenate(A), np.concatenate(B), np.concatenate(Q)
+    perm = np.random.default_rng(11).permutation(len(Q))
+    A, B, Q = np.ascontiguousarray(A[perm]), np.ascontiguousarray(B[perm]), Q[perm]
+    r = ctx.reconcile_packed(code, capi.make_params(32, 50, 100.0, True, fast_math=True), A, B, Q, want_syndrome=True)
+    monkeypatch.setenv("QLB_SPLIT_MAX_BUNDLES", "2")
+    s = ctx.reconcile_packed(code, capi.make_params(32, 50, 100.0, True, fast_math=True, tier=3), A, B, Q, want_syndrome=True)
+    assert all((x == y).all() for x, y in zip(r, s))
+
+
 def test_streaming_kernel_large_block_length(ctx, oracle):
     """N = 100 000 in fp32 goes through the streaming kernel by default; flags must equal the fp64 oracle's."""
     n, m = 100000, 51080
