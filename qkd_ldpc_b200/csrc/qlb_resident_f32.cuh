@@ -95,6 +95,13 @@ namespace qlb
         // forming B_k - A_k directly. A denominator rounded to zero gives +inf, one rounded below zero gives NaN out of
         // lg2; fminf(NaN or +inf, cap) = cap, so both saturate to the clamp exactly like a saturated product (:246-249).
         static constexpr float kUnit = 1.4426950408889634f; // messages = LLR * kUnit
+        // The parity-first look (decode_resident_f32_kernel) pays for the rules whose check pass is expensive -- fp32 accurate
+        // +7 %, fp64 +36 % frames/s at QBER 0.03 -- but not for this one: +0.6 % at QBER 0.03, -1.5 % at 0.09 (B200, 14 800
+        // frames; its extra live state costs the 64-register hot loops more than the skipped 108-instruction pass returns).
+#ifndef QLB_F32FAST_PARITY_FIRST
+#define QLB_F32FAST_PARITY_FIRST 0
+#endif
+        static constexpr bool kParityFirst = QLB_F32FAST_PARITY_FIRST != 0;
         template <int W>
         static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, float cap)
         {
@@ -123,6 +130,7 @@ namespace qlb
     struct RuleF32Accurate
     {
         static constexpr float kUnit = 1.f; // natural-log units
+        static constexpr bool kParityFirst = true;
         // libdevice tanhf / atanhf, leave-one-out product by prefix * suffix
         template <int W>
         static __device__ __forceinline__ void apply(float (&v)[W], uint32_t xr, float cap)
@@ -204,6 +212,7 @@ namespace qlb
     }
 
     constexpr int kResidentMaxCW = 16;
+    constexpr int kQuietChecks = 16; // at most this many threads saw an unsatisfied check: the frame is about to converge
     constexpr int kBitUnroll = 1; // bits per thread in flight in the bit pass (2 measured no faster: the pass is bandwidth-, not latency-bound)
 #ifndef QLB_RESIDENT_MAX_THREADS
 #define QLB_RESIDENT_MAX_THREADS 1024
@@ -265,6 +274,28 @@ namespace qlb
             bs += kThreads;
             zw += kThreads >> 5;
         }
+    }
+
+    // Parity of the riding hard decisions against the target syndrome for every check this thread visits -- the convergence test
+    // of :277-298 on its own, without the check rule. Bit 0 of the result: some check of this thread fails. Out of line: it runs
+    // once or twice per converging frame and must not cost the hot loops a register.
+    static __device__ __noinline__ uint32_t parity_walk(const int kThreads, const unsigned char *__restrict__ msg_bytes, const uint32_t *s_base4,
+                                                        const uint32_t *s_seg_w, const uint32_t *s_seg_lo, const uint32_t *s_seg_hi, int nseg, uint32_t my_syn)
+    {
+        uint32_t bad = 0;
+        int r = 0;
+        for (int sg = 0; sg < nseg; ++sg)
+        {
+            const int w = (int)s_seg_w[sg];
+            for (uint32_t p = s_seg_lo[sg] + threadIdx.x; p < s_seg_hi[sg]; p += kThreads, ++r)
+            {
+                uint32_t x = my_syn >> r;
+                for (int k = 0; k < w; ++k)
+                    x ^= *reinterpret_cast<const uint32_t *>(msg_bytes + s_base4[k] + 4u * p);
+                bad |= x;
+            }
+        }
+        return bad & 1u;
     }
 
     // kBW: the (uniform) bit weight. Host-checked requirements: slots < 65535, max_check_w <= 16, every bit of weight kBW,
@@ -424,10 +455,18 @@ namespace qlb
             // ---- iterations ----------------------------------------------------------------------------------------
             // `it` counts completed bit passes. The check pass of round `it` also evaluates the parity of the hard
             // decisions of bit pass `it` (meaningless for it == 0: bit 0 then still holds Alice's / zero bits).
+            // A converged frame would otherwise pay one more full check pass just to learn it. When the previous check pass saw only
+            // a handful of unsatisfied checks -- the signature of the last rounds of a converging frame, never of a failing one,
+            // which keeps hundreds of them -- the parity is looked at on its own first (~1/4 of a check pass).
             int it = 0;
-            bool success = false;
+            bool success = false, quiet = false;
             for (;;)
             {
+                if (Rule::kParityFirst && quiet && it > 0 && !__syncthreads_or((int)parity_walk(kThreads, msg_bytes, s_base4, s_seg_w, s_seg_lo, s_seg_hi, nseg, s_park_syn[tid])))
+                {
+                    success = true; // :285-298
+                    break;
+                }
                 uint32_t bad = 0;
                 {
                     const uint32_t my_syn = s_park_syn[tid];
@@ -451,12 +490,13 @@ namespace qlb
                         }
                     }
                 }
-                const int any_bad = __syncthreads_or((int)(bad & 1u));
+                const int any_bad = __syncthreads_count((int)(bad & 1u)); // threads with an unsatisfied check
                 if (it > 0 && !any_bad)
                 {
                     success = true; // the decisions of bit pass `it` satisfy the syndrome (:285-298)
                     break;
                 }
+                quiet = Rule::kParityFirst && it > 0 && any_bad <= kQuietChecks;
                 if (it == args.max_it)
                     break; // :337-344
                 if (clamp_b2c)
