@@ -59,6 +59,7 @@ namespace qlb
         uint32_t *src_of;   // [n_groups][G] repack plan: old column id (g * G + column) that moves to new column id k
         uint32_t *fmap_new; // [n_groups][G]
         uint32_t *repack;   // [0] repack decided, [1] live frames, [2] groups after the repack
+        int repack_pct;     // repack when the live columns are at most this percentage of the streamed ones
     };
     constexpr uint32_t kNoFrame = 0xFFFFFFFFu;
     constexpr int kMaxRepackGroups = 256; // per wave: the bit-array move stages one word per group and frame word in shared memory
@@ -635,8 +636,8 @@ namespace qlb
         }
         __syncthreads();
         const uint32_t live = s_cnt[ng], new_groups = (live + G - 1) / G;
-        // worth it when at most half of the streamed columns are live and at least one group disappears
-        const bool go = live > 0 && 2u * live <= s_live_groups * (uint32_t)G && new_groups < s_live_groups;
+        // worth it when enough of the streamed columns are dead (repack_pct) and at least one group disappears
+        const bool go = live > 0 && 100ull * live <= (unsigned long long)st.repack_pct * s_live_groups * G && new_groups < s_live_groups;
         if (!go)
             return;
         if (tid < ng)

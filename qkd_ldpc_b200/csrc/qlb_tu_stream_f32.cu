@@ -68,6 +68,10 @@ namespace
         st.bundles = static_cast<unsigned char *>(ctx->scratch.p);
         st.bundle_stride = per_bundle;
         st.bundle = B;
+        st.repack_pct = 65; // measured on B200, N = 100 000: 50 / 65 / 80 / 90 % -> 0.664 / 0.694 / 0.686 / 0.651 of peak at QBER 0.085
+        if (const char *e = std::getenv("QLB_SPLIT_REPACK_PCT")) // experiments
+            if (std::atoi(e) > 0 && std::atoi(e) < 100)
+                st.repack_pct = std::atoi(e);
         uint32_t *words = reinterpret_cast<uint32_t *>(st.bundles + (size_t)bundles_per_wave * per_bundle);
         st.act = words;
         st.bad = words + 4 * per_wave;
@@ -95,7 +99,11 @@ namespace
         auto k_commit = stream_repack_commit_kernel<VEC>;
         // rounds after which a repack is attempted (decided on the device: live columns <= half of the streamed ones)
         const bool repack_on = !std::getenv("QLB_SPLIT_NO_REPACK") && per_wave <= kMaxRepackGroups && per_wave >= 2;
-        auto repack_round = [](int it) { return it >= 6 && it % 4 == 2; }; // an attempt that decides against costs ~15 us
+        int repack_every = 4;
+        if (const char *e = std::getenv("QLB_SPLIT_REPACK_EVERY")) // experiments
+            if (std::atoi(e) > 0)
+                repack_every = std::atoi(e);
+        auto repack_round = [repack_every](int it) { return it >= 4 && it % repack_every == 2 % repack_every; }; // a declined attempt costs ~15 us
         int occ_check = 1, occ_bit = 1;
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_check, k_check, kSplitCheckThreads, 0));
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bit, k_bit, kSplitBitThreads, 0));
