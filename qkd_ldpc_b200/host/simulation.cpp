@@ -9,6 +9,7 @@
 // over the GPUs with one NCCL all-reduce per point (qlb_stats_allreduce).
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <condition_variable>
 #include <deque>
@@ -335,6 +336,12 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
 {
     using clock = std::chrono::steady_clock;
     const auto t_start = clock::now();
+    const bool timing = std::getenv("QKD_B200_TIMING") != nullptr; // coarse wall-clock marks on stderr
+    auto mark = [&](const char *what)
+    {
+        if (timing)
+            std::fprintf(stderr, "[timing] %8.3f s  %s\n", std::chrono::duration<double>(clock::now() - t_start).count(), what);
+    };
     const size_t trials = CFG.TRIALS_NUMBER;
     size_t points_total = 0;
     for (const sim_input &in : sim_in)
@@ -347,6 +354,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     for (size_t &s : seeds)
         s = any_size(seed_prng);
 
+    mark("trial seeds drawn");
     int gpus = qkd_b200::usable_devices();
     if (gpus < 1)
         throw std::runtime_error("no CUDA device is available: this build has no CPU decoder");
@@ -398,6 +406,8 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                                  {
             try { contexts[g] = qkd_b200::context(g % gpus); } // worker g drives GPU g % gpus with its own context
             catch (const std::exception &e) { std::lock_guard<std::mutex> lk(err_mu); if (first_error.empty()) first_error = e.what(); }
+            if (g == workers - 1)
+                mark("last worker has its context");
             for (;;)
             {
                 batch *b = ready.pop();
@@ -444,16 +454,43 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 }
                 done_cv.notify_all();
             } });
+    // The sweep's ONE collective is a single NCCL all-reduce of the integer statistics of every point, at the end. Creating
+    // the communicators takes seconds on an 8-GPU box, so it happens on a side thread (with contexts of its own) while the
+    // GPUs decode.
+    const bool reduce_over_nccl = gpus > 1 || std::getenv("QKD_B200_FORCE_ALLREDUCE");
+    std::vector<std::vector<uint64_t>> sweep_stats(gpus, std::vector<uint64_t>(points_total * stats_width, 0));
+    std::string warm_error;
+    std::thread nccl_warm_up;
+    if (reduce_over_nccl)
+        nccl_warm_up = std::thread([&]
+                                   {
+            try
+            {
+                std::vector<qlb_ctx *> ctxs;
+                std::vector<uint64_t> zero(gpus, 0);
+                std::vector<uint64_t *> ptrs;
+                for (int g = 0; g < gpus; ++g)
+                {
+                    ctxs.push_back(qkd_b200::context(g));
+                    ptrs.push_back(&zero[g]);
+                }
+                qkd_b200::check(qlb_stats_allreduce(ctxs.data(), gpus, ptrs.data(), 1), "qlb_stats_allreduce (communicator set-up)");
+                mark("NCCL communicators ready");
+            }
+            catch (const std::exception &e) { warm_error = e.what(); } });
     auto shut_down = [&]
     {
         for (int g = 0; g < workers; ++g)
             ready.push(nullptr);
         for (auto &t : gpu_threads)
             t.join();
+        if (nccl_warm_up.joinable())
+            nccl_warm_up.join();
     };
 
     std::vector<sim_result> sim_results(points_total);
     size_t curr_sim = 0, frames_total = 0, iterations_total = 0;
+    std::vector<size_t> point_ok_sp, point_ok_ldpc;
     g_report = qkd_b200::sweep_report{};
     try
     {
@@ -462,6 +499,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
             const H_matrix &matrix = in.matrix;
             const size_t n = matrix.num_bit_nodes, words = (n + 31) / 32;
             code = qkd_b200::code_for(matrix);
+            mark("code layout ready");
             const std::string matrix_filename = in.matrix_path.filename().string();
             for (const double QBER : in.QBER)
             {
@@ -513,20 +551,15 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 }
                 if (!first_error.empty())
                     throw std::runtime_error(first_error);
+                mark("point decoded");
 
-                // the sweep's one collective: sum the per-GPU integer statistics (NCCL all-reduce over the GPUs of this box)
-                for (int w = gpus; w < workers; ++w) // fold the second worker of each GPU into the first
+                // fold the second worker of each GPU into the first and keep the point's per-GPU integer statistics for the
+                // all-reduce at the end of the sweep
+                for (int w = gpus; w < workers; ++w)
                     for (size_t x = 0; x < stats_width; ++x)
                         gpu_stats[w % gpus][x] += gpu_stats[w][x];
-                std::vector<uint64_t> reduced = gpu_stats[0];
-                if (gpus > 1 || std::getenv("QKD_B200_FORCE_ALLREDUCE"))
-                {
-                    std::vector<uint64_t *> ptrs;
-                    for (int g = 0; g < gpus; ++g)
-                        ptrs.push_back(gpu_stats[g].data());
-                    qkd_b200::check(qlb_stats_allreduce(contexts.data(), gpus, ptrs.data(), stats_width), "qlb_stats_allreduce");
-                    reduced = gpu_stats[0];
-                }
+                for (int g = 0; g < gpus; ++g)
+                    std::copy(gpu_stats[g].begin(), gpu_stats[g].end(), sweep_stats[g].begin() + static_cast<std::ptrdiff_t>(curr_sim * stats_width));
 
                 // statistics exactly as the reference accumulates them, in trial order (src/simulation.cpp:252-312)
                 size_t ok_sp = 0, ok_ldpc = 0, it_max = 0, it_min = max_it;
@@ -549,8 +582,8 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                             sd += pow(static_cast<double>(tr.ldpc_res.sp_res.iterations_num) - mean, 2);
                     sd = sqrt(sd / static_cast<double>(ok_sp));
                 }
-                if (reduced[max_it + 1] != ok_sp || reduced[max_it + 2] != ok_ldpc || reduced[max_it + 3] != trials)
-                    throw std::runtime_error("reduced statistics disagree with the per-trial results");
+                point_ok_sp.push_back(ok_sp);
+                point_ok_ldpc.push_back(ok_ldpc);
 
                 sim_result &r = sim_results[curr_sim];
                 r.sim_number = curr_sim;
@@ -566,7 +599,6 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 r.ratio_trials_successful_ldpc = static_cast<double>(ok_ldpc) / trials;
                 r.ratio_trials_successful_sp = static_cast<double>(ok_sp) / trials;
                 frames_total += trials;
-                iterations_total += reduced[max_it + 4];
                 qkd_b200::point_report pr;
                 pr.sim_number = curr_sim;
                 pr.matrix_filename = matrix_filename;
@@ -574,9 +606,10 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 pr.num_check_nodes = matrix.num_check_nodes;
                 pr.exact_qber = r.initial_QBER;
                 pr.frames = trials;
-                pr.frame_iterations = reduced[max_it + 4];
+                pr.frame_iterations = 0; // filled from the reduced statistics below
                 pr.seconds = std::chrono::duration<double>(clock::now() - t_point).count();
                 g_report.points.push_back(pr);
+                mark("point statistics done");
                 ++curr_sim;
             }
         }
@@ -587,6 +620,34 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
         throw;
     }
     shut_down();
+
+    // ---- the sweep's one collective: SUM all-reduce of [points x (max_it + 5)] integers over the GPUs of this box -----------
+    if (reduce_over_nccl && !traced)
+    {
+        if (!warm_error.empty())
+            throw std::runtime_error(warm_error);
+        std::vector<qlb_ctx *> ctxs;
+        std::vector<uint64_t *> ptrs;
+        for (int g = 0; g < gpus; ++g)
+        {
+            ctxs.push_back(qkd_b200::context(g));
+            ptrs.push_back(sweep_stats[g].data());
+        }
+        qkd_b200::check(qlb_stats_allreduce(ctxs.data(), gpus, ptrs.data(), sweep_stats[0].size()), "qlb_stats_allreduce");
+        mark("statistics all-reduced");
+    }
+    else
+        for (int g = 1; g < gpus; ++g)
+            for (size_t x = 0; x < sweep_stats[0].size(); ++x)
+                sweep_stats[0][x] += sweep_stats[g][x];
+    for (size_t pt = 0; pt < curr_sim; ++pt)
+    {
+        const uint64_t *reduced = sweep_stats[0].data() + pt * stats_width;
+        if (reduced[max_it + 1] != point_ok_sp[pt] || reduced[max_it + 2] != point_ok_ldpc[pt] || reduced[max_it + 3] != trials)
+            throw std::runtime_error("reduced statistics disagree with the per-trial results");
+        g_report.points[pt].frame_iterations = reduced[max_it + 4];
+        iterations_total += reduced[max_it + 4];
+    }
 
     g_report.seconds_total = std::chrono::duration<double>(clock::now() - t_start).count();
     g_report.seconds_device = device_ns.load() * 1e-9 / workers;
