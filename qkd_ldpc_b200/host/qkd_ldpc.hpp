@@ -162,6 +162,7 @@ namespace qkd_b200
     {
         double seconds_total{};
         double seconds_device{};
+        double seconds_startup{}; // from entry until every GPU worker holds its context (driver + context initialisation)
         size_t frames{};
         size_t frame_iterations{};
         int gpus{};

@@ -360,7 +360,10 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
         throw std::runtime_error("no CUDA device is available: this build has no CPU decoder");
     if (CFG.DEVICE_GPUS > 0)
         gpus = std::min(gpus, CFG.DEVICE_GPUS);
-    const size_t batch_frames = std::max<size_t>(1, CFG.DEVICE_BATCH_FRAMES);
+    // device_batch_frames is the upper bound; with many GPUs the batches shrink so that every worker still gets ~8 of them per
+    // QBER point (the point ends with a barrier: 61 batches over 16 workers would leave a quarter of them idle at the end)
+    const size_t batch_cap = std::max<size_t>(1, CFG.DEVICE_BATCH_FRAMES);
+    const size_t batch_frames = std::min(batch_cap, std::max<size_t>(1024, trials / (static_cast<size_t>(gpus) * 2 * 8) + 1));
     const size_t max_it = CFG.SUM_PRODUCT_MAX_ITERATIONS;
     const qlb_decode_params params = qkd_b200::params_from_cfg(max_it, CFG.SUM_PRODUCT_MSG_LLR_THRESHOLD);
     const size_t stats_width = max_it + 1 + 4; // histogram of iterations of successful frames + {n_sp, n_ldpc, n_trials, sum_iterations}
@@ -383,7 +386,8 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     std::condition_variable done_cv;
     std::string first_error;
     qlb_code *code = nullptr;                 // the current matrix
-    std::atomic<uint64_t> device_ns{0};
+    std::atomic<uint64_t> device_ns{0}, ready_ns{0};
+    std::atomic<int> contexts_ready{0};
     std::vector<std::thread> gpu_threads;
     // integer statistics of one finished trial: histogram of iterations of successful frames + {n_sp, n_ldpc, n_trials, sum_iterations}
     auto account = [max_it](std::vector<uint64_t> &st, const trial_result &tr)
@@ -406,8 +410,11 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                                  {
             try { contexts[g] = qkd_b200::context(g % gpus); } // worker g drives GPU g % gpus with its own context
             catch (const std::exception &e) { std::lock_guard<std::mutex> lk(err_mu); if (first_error.empty()) first_error = e.what(); }
-            if (g == workers - 1)
-                mark("last worker has its context");
+            if (++contexts_ready == workers)
+            {
+                ready_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(clock::now() - t_start).count();
+                mark("every worker has its context");
+            }
             for (;;)
             {
                 batch *b = ready.pop();
@@ -651,6 +658,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
 
     g_report.seconds_total = std::chrono::duration<double>(clock::now() - t_start).count();
     g_report.seconds_device = device_ns.load() * 1e-9 / workers;
+    g_report.seconds_startup = ready_ns.load() * 1e-9; // CUDA initialisation + contexts: ~1 s on a 1-GPU box, ~8 s on an 8-GPU box
     g_report.frames = frames_total;
     g_report.frame_iterations = iterations_total;
     g_report.gpus = gpus;
