@@ -76,7 +76,8 @@ struct config_data
     bool DEVICE_FP32_FAST = false; // "device_fp32_fast_math": SFU check rule for fp32
     bool DEVICE_FP64_FUSED = false; // "device_fp64_fused_ratio": one-division form of the fp64 check rule (QLB_FLAG_F64_FUSED_RATIO)
     int DEVICE_GPUS = 0;           // "device_gpus": 0 = all visible GPUs
-    size_t DEVICE_BATCH_FRAMES = 4096; // "device_batch_frames": frames per launch handed to one GPU
+    size_t DEVICE_BATCH_FRAMES = 32768; // "device_batch_frames": most frames per launch handed to one GPU (the on-device key generator needs
+                                        // >= 32 k trials in flight to reach its 2.2 M frames/s: 4 096 -> 0.67 M, 16 384 -> 1.83 M; scripts/gen_timing2.py)
     bool DEVICE_GENERATE_KEYS = true;  // "device_generate_keys": draw Alice/Bob on the GPU from the trial seeds (bit-exact with
                                        // generate_random_bit_array / introduce_errors); false = host threads generate
 };
