@@ -56,8 +56,8 @@ enum {
     QLB_FLAG_F32_FAST_MATH = 1, /* fp32 only: exp-domain check rule on MUFU ex2/lg2/rcp instead of tanhf/atanhf */
     /* fp64 only: the check rule src/qkd_ldpc_algorithm.cpp:220-243 evaluated as ln((S - e D) / (D - e S)) -- one exp, one
      * division, one log per edge instead of tanh, divide, atanh. Same function, different rounding near saturation; honoured
-     * by the SM-resident fp64 kernel (the generic kernel keeps the literal order). Per-frame outcomes validated against the
-     * reference in profiles/parity_r01.md. */
+     * by the SM-resident fp64 kernel and by the generic kernel (checks wider than its unrolled shapes keep the literal order).
+     * Per-frame outcomes validated against the reference in profiles/parity_r01.md and on the exhaustive small-code fixtures. */
     QLB_FLAG_F64_FUSED_RATIO = 2,
     /* test hook, bits 8..11 = 1 + storage tier (0 shared memory, 1 L2 scratch for messages, 2 all global): run the generic
      * kernel in that tier instead of the fastest eligible one; ignored when the tier does not fit */

@@ -228,7 +228,8 @@ namespace
         if (p->precision == QLB_PRECISION_F64 && forced < 0 && resident_f64_eligible(ctx, args.code))
             return launch_resident_f64(ctx, args, kReconcile, (p->flags & QLB_FLAG_F64_FUSED_RATIO) != 0);
         if (p->precision == QLB_PRECISION_F64)
-            return launch_tier<MathF64, kReconcile>(ctx, args, forced);
+            return (p->flags & QLB_FLAG_F64_FUSED_RATIO) ? launch_tier<MathF64Fused, kReconcile>(ctx, args, forced)
+                                                         : launch_tier<MathF64, kReconcile>(ctx, args, forced);
         if (fast)
             return launch_tier<MathF32Fast, kReconcile>(ctx, args, forced);
         return launch_tier<MathF32, kReconcile>(ctx, args, forced);

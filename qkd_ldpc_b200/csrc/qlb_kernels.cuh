@@ -281,6 +281,10 @@ namespace qlb
         static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(MathF64::two_atanh(p), thr, en); }
     };
     template <>
+    struct TwoPass<MathF64Fused> : TwoPass<MathF64> // checks wider than the unrolled shapes keep the literal order
+    {
+    };
+    template <>
     struct TwoPass<MathF32>
     {
         static constexpr bool kZeroAware = true;

@@ -136,7 +136,7 @@ def test_sweep_grid_identical(ctx, dev_codes, oracle, graphs, precision, fast):
 
 
 @pytest.mark.parametrize("name", ["dense_n6_m4", "dense_n7_m3", "dense_n10_m5"])
-@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("precision", [64, "64fused", 32])
 def test_small_codes_exhaustive(ctx, dev_codes, graphs, name, precision):
     """Every Alice x every single-bit error on the shipped dense codes, against the reference's own outputs."""
     z = np.load(GOLD / "small_codes.npz")[name]
@@ -146,7 +146,9 @@ def test_small_codes_exhaustive(ctx, dev_codes, graphs, name, precision):
     a = ((z[:, 0:1] >> np.arange(n)) & 1).astype(np.int32)
     b = a.copy()
     b[np.arange(len(z)), z[:, 1]] ^= 1
-    p = capi.make_params(precision, 100, 100.0, True)
+    fused = precision == "64fused"  # the one-division fp64 rule, here through the generic kernel (these codes take no resident kernel)
+    precision = 64 if fused else precision
+    p = capi.make_params(precision, 100, 100.0, True, fast_math=fused)
     it, res, dec, syn = ctx.reconcile(code, p, a, b, 1.0 / n, want_syndrome=True)
     dv = (dec.astype(np.int64) << np.arange(n)).sum(1)
     sv = (syn.astype(np.int64) << np.arange(g.m)).sum(1)
