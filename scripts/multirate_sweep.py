@@ -13,7 +13,7 @@ threads = os.cpu_count() or 8
 orc = Restatement(); ctx = capi.Context(0)
 h2 = lambda q: -q * math.log2(q) - (1 - q) * math.log2(1 - q)
 plan = {7168: [0.10, 0.12, 0.13, 0.14, 0.16], 5231: [0.06, 0.075, 0.0825, 0.0875, 0.095], 3072: [0.03, 0.038, 0.042, 0.046, 0.055], 2048: [0.012, 0.018, 0.021, 0.024, 0.03]}
-variants = {"f64": capi.make_params(64, 100, 100.0, True), "f32": capi.make_params(32, 100, 100.0, True), "f32fast": capi.make_params(32, 100, 100.0, True, fast_math=True)}
+variants = {"f64": capi.make_params(64, 100, 100.0, True), "f64fused": capi.make_params(64, 100, 100.0, True, fast_math=True), "f32": capi.make_params(32, 100, 100.0, True), "f32fast": capi.make_params(32, 100, 100.0, True, fast_math=True)}
 seeds0 = orc.trial_seeds(424242, per)
 for m, qs in plan.items():
     mat = codes.peg_code(10240, m, 3, 666)
