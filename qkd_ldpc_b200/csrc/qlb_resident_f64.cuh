@@ -41,8 +41,19 @@ namespace qlb
 
     // All checks of weight exactly W in [lo, hi). zsrc: packed bits whose parity per check is wanted (the last hard decision,
     // or Alice's key during the first pass, which yields her syndrome: src/qkd_ldpc_algorithm.cpp:413-414).
-    template <typename Math, int W>
-    __device__ __forceinline__ uint32_t check_segment64(int kThreads, const Split64 &msg, const DecodeArgs &args, const uint16_t *__restrict__ col_of_slot,
+    struct Base64FromParams
+    {
+        const DecodeArgs &args;
+        __device__ __forceinline__ uint32_t operator()(int k) const { return args.code.base[k]; }
+    };
+    struct Base64FromSmem
+    {
+        const uint32_t *base;
+        __device__ __forceinline__ uint32_t operator()(int k) const { return base[k]; }
+    };
+
+    template <typename Math, int W, typename Base>
+    __device__ __forceinline__ uint32_t check_segment64(int kThreads, const Split64 &msg, const Base base, const uint16_t *__restrict__ col_of_slot,
                                                         const uint32_t *__restrict__ zsrc, uint32_t lo, uint32_t hi, uint32_t &my_syn, int &rbit,
                                                         bool first, bool en, double thr)
     {
@@ -55,7 +66,7 @@ namespace qlb
 #pragma unroll
             for (int k = 0; k < W; ++k)
             {
-                const uint32_t slot = args.code.base[k] + p;
+                const uint32_t slot = base(k) + p;
                 const uint32_t col = col_of_slot[slot];
                 par ^= zsrc[col >> 5] >> (col & 31);
                 v[k] = msg.ld(slot);
@@ -75,12 +86,24 @@ namespace qlb
             Math::template check<W>(v, W, sb != 0, en, thr);
 #pragma unroll
             for (int k = 0; k < W; ++k)
-                msg.st(args.code.base[k] + p, v[k]);
+                msg.st(base(k) + p, v[k]);
         }
         return bad;
     }
 
-    // kBW: uniform bit weight. Host-checked: slots < 65535, n < 65536, max_check_w <= 8, n % 32 == 0, n, m <= 32 * kThreads.
+    // Weights 9..16 (the R >= 0.7 codes of the CW = 3 family) are kept out of line: their register appetite (2 x W doubles live) must
+    // not leak into the hot instantiations; some spilling inside them is still far cheaper than the generic kernel's L2 round trips.
+    // Returns {bit 0: parity failure, bits 1..: advanced round counter} and the (first pass) accumulated syndrome bits.
+    template <typename Math, int W>
+    __device__ __noinline__ uint2 check_segment64_wide(int kThreads, const Split64 msg, const uint32_t *s_base, const uint16_t *col_of_slot,
+                                                       const uint32_t *zsrc, uint32_t lo, uint32_t hi, uint32_t my_syn, int rbit, bool first, bool en,
+                                                       double thr)
+    {
+        const uint32_t bad = check_segment64<Math, W>(kThreads, msg, Base64FromSmem{s_base}, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr);
+        return make_uint2((bad & 1u) | ((uint32_t)rbit << 1), my_syn);
+    }
+
+    // kBW: uniform bit weight. Host-checked: slots < 65535, n < 65536, max_check_w <= 16, n % 32 == 0, n, m <= 32 * kThreads.
     template <typename Math, bool kReconcile, int kBW, int kMaxThreads>
     __global__ void __launch_bounds__(kMaxThreads, 1) decode_resident_f64_kernel(const DecodeArgs args, uint32_t smem_slots,
                                                                                  const uint16_t *__restrict__ col_of_slot)
@@ -89,6 +112,7 @@ namespace qlb
         extern __shared__ __align__(16) unsigned char smem[];
         __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
         __shared__ uint32_t s_park_bob[kMaxThreads], s_park_syn[kMaxThreads];
+        __shared__ uint32_t s_base[kResidentMaxCW];
         __shared__ int s_nseg;
         __shared__ long long s_frame;
 
@@ -96,6 +120,8 @@ namespace qlb
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31;
         const int words_n = code.words_n, words_m = code.words_m;
         const size_t wn = align_up((size_t)words_n * 4, 16);
+        if (tid < kResidentMaxCW)
+            s_base[tid] = code.base[tid];
 
         Split64 msg;
         msg.smem = reinterpret_cast<double *>(smem);
@@ -240,9 +266,13 @@ namespace qlb
                         const uint32_t lo = s_seg_lo[sg], hi = s_seg_hi[sg];
                         switch (s_seg_w[sg])
                         {
-#define QLB_SEG64(W_) case W_: bad |= check_segment64<Math, W_>(kThreads, msg, args, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); break;
+#define QLB_SEG64(W_) case W_: bad |= check_segment64<Math, W_>(kThreads, msg, Base64FromParams{args}, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); break;
+#define QLB_SEG64W(W_) case W_: { const uint2 rv = check_segment64_wide<Math, W_>(kThreads, msg, s_base, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); \
+                                  bad |= rv.x & 1u; rbit = (int)(rv.x >> 1); my_syn = rv.y; } break;
                             QLB_SEG64(1) QLB_SEG64(2) QLB_SEG64(3) QLB_SEG64(4) QLB_SEG64(5) QLB_SEG64(6) QLB_SEG64(7) QLB_SEG64(8)
+                            QLB_SEG64W(9) QLB_SEG64W(10) QLB_SEG64W(11) QLB_SEG64W(12) QLB_SEG64W(13) QLB_SEG64W(14) QLB_SEG64W(15) QLB_SEG64W(16)
 #undef QLB_SEG64
+#undef QLB_SEG64W
                         default: // checks without edges: satisfied only by a zero syndrome bit
                             for (uint32_t p = lo + tid; p < hi; p += kThreads, ++rbit)
                                 if (!first)

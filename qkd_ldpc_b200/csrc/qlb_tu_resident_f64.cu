@@ -15,7 +15,7 @@ namespace
     bool resident64_eligible_impl(const qlb_ctx *ctx, const CodeDev &c)
     {
         return c.slots < 65535 && c.n < 65536 && c.bit_slots16 && c.col_of_slot16 && c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 &&
-               c.max_check_w <= 8 && c.n % 32 == 0 && balanced_block_size(c, kResident64Threads, 0.85, kResident64Threads * 3 / 4, 0.05) > 0 &&
+               c.max_check_w <= kResidentMaxCW && c.n % 32 == 0 && balanced_block_size(c, kResident64Threads, 0.85, kResident64Threads * 3 / 4, 0.05) > 0 &&
                (size_t)ctx->smem_optin > kResident64StaticSmem + resident64_small_bytes(c.n, c.m) + 8192 &&
                resident64_smem_slots(ctx, c) >= (uint32_t)c.slots / 2;
     }
