@@ -168,7 +168,7 @@ def workload_config(frames_per_point, precision):
                     f"{frames_per_point} frames per point per GPU",
         "code": "N=10240 M=5231 E=30720 CW=3", "qber_grid": [round(q, 4) for q in qber_grid()],
         "frames_per_point_per_gpu": frames_per_point, "max_iterations": MAX_IT, "msg_threshold": THR,
-        "precision": precision, "parallelism": "trial-sharded (one process per GPU, no data-path collective)",
+        "precision": precision, "parallelism": "trial-sharded (one process per GPU, no data-path collective); the 9 launches of a sweep alternate between two streams of the GPU",
         "l2_policy": "inputs larger than L2 (packed keys of one sweep > 126 MB) and a fresh key set per QBER point",
     }
 
@@ -242,13 +242,25 @@ def main():
     h_res = torch.zeros((len(grid), fpp), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    # a second context (stream, frame queue) on the same GPU: the points of a sweep alternate between the two streams, so the
+    # tail of one point's launch (SMs running out of frames) is filled by the next point's CTAs. Fork / join through events,
+    # so that the CUDA events timed() records on ctx's stream still bracket everything.
+    ctx_b = capi.Context(local_rank)
+    ext_b = torch.cuda.ExternalStream(ctx_b.stream, device=dev)
+    launch_order = sorted(range(len(grid)), key=lambda pt: -grid[pt])  # the long (non-converging) points first
 
     def sweep_step(prec, frames=fpp, collect=True):
-        """One step on device-resident inputs: 9 launches on the context's stream, then results -> host -> statistics."""
+        """One step on device-resident inputs: 9 launches over the two streams, then results -> host -> statistics."""
         p = params_for(prec)
-        for pt in range(len(grid)):
+        fork = torch.cuda.Event()
+        fork.record(ext)
+        ext_b.wait_event(fork)
+        for i, pt in enumerate(launch_order):
             a, b, lp, _ = keys[pt]
-            ctx.reconcile_device(code, p, frames, a.data_ptr(), b.data_ptr(), lp.data_ptr(), d_it[pt].data_ptr(), d_res[pt].data_ptr())
+            (ctx if i % 2 == 0 else ctx_b).reconcile_device(code, p, frames, a.data_ptr(), b.data_ptr(), lp.data_ptr(), d_it[pt].data_ptr(), d_res[pt].data_ptr())
+        join = torch.cuda.Event()
+        join.record(ext_b)
+        ext.wait_event(join)
         if not collect:
             return None
         with torch.cuda.stream(ext):
@@ -290,8 +302,9 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.counters(reset=True)
+    ctx_b.counters(reset=True)
     ms_total, wall_total, stats = timed(lambda: sweep_step(prec), args.steps)
-    launches, frame_iters = ctx.counters(reset=True)
+    launches, frame_iters = (x + y for x, y in zip(ctx.counters(reset=True), ctx_b.counters(reset=True)))
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     frames_step = fpp * len(grid) * world
@@ -375,7 +388,6 @@ def main():
     # scheduler does with its two workers per GPU: one point's H2D / D2H copies run under the other point's decode. The calls
     # are the blocking C-ABI entry point; ctypes releases the GIL while they run.
     from concurrent.futures import ThreadPoolExecutor
-    ctx_b = capi.Context(local_rank)
     e2e_pool = ThreadPoolExecutor(max_workers=2)
 
     def e2e_points(c, points):
