@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QLB_VERSION 100 /* 0.1.0 */
+#define QLB_VERSION 200 /* 0.2.0: qlb_decode_params grew execution knobs (was 24 bytes, now 40) */
 
 /* status codes (0 = ok); qlb_last_error() gives the message of the calling thread's last failure */
 enum {
@@ -75,6 +75,12 @@ typedef struct qlb_decode_params {
     int32_t enable_threshold; /* CFG.ENABLE_SUM_PRODUCT_MSG_LLR_THRESHOLD                           */
     int32_t flags;            /* QLB_FLAG_*                                                        */
     double threshold;         /* CFG.SUM_PRODUCT_MSG_LLR_THRESHOLD, > 0 when enabled                */
+    /* Execution knobs with no effect on results (0 = library default). They replace what used to be environment
+     * variables: a drop-in library is steered through its arguments only. */
+    int32_t stream_max_bundles; /* streaming decoder: at most this many 4-group bundles per wave (default: what device memory holds) */
+    int32_t stream_no_repack;   /* streaming decoder: 1 = no on-device compaction of the live frames                  */
+    int32_t block_threads;      /* SM-resident decoders: threads per CTA (multiple of 32; ignored when inadmissible)   */
+    int32_t reserved;           /* must be 0                                                                           */
 } qlb_decode_params;
 
 /* Per-frame result of a decode; mirrors SP_result / LDPC_result (src/qkd_ldpc_algorithm.hpp:14-24). */
@@ -205,6 +211,12 @@ int qlb_generate_device(qlb_ctx *ctx, int32_t n_bits, int64_t n_frames, const ui
  * only 8 bytes per frame go up and 5 come back. Host buffers. */
 int qlb_run_trials(qlb_ctx *ctx, const qlb_code *code, const qlb_decode_params *params, int64_t n_frames, const uint64_t *seeds,
                    uint64_t seed_offset, double qber, uint32_t *iterations_out, uint8_t *result_out, double *exact_qber_out);
+
+/* Test probe (no reference counterpart): the fp64 building blocks of the check rule, element-wise over host arrays, so that
+ * their accuracy against the host libm is a test and not a claim. op 0: a / b (the rule's own division), 1: e^a for a in
+ * [-64, 0], 2: ln(a / b) for 0 < b <= a, 3: tanh(a / 2), 4: 2 atanh(a) (b != 0: IEEE infinities at |a| = 1). b may be NULL for
+ * the unary ops. */
+int qlb_test_f64_math(qlb_ctx *ctx, int op, int64_t n, const double *a, const double *b, double *out);
 
 /* ---- sweep statistics ---------------------------------------------------------------------------
  * The one collective of a sweep: element-wise SUM over the GPUs of one process of per-GPU integer statistics

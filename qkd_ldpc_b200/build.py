@@ -46,7 +46,7 @@ def _run(cmd, log_name):
         raise RuntimeError(f"build failed: {' '.join(str(c) for c in cmd)}")
 
 
-TRANSLATION_UNITS = ["qlb_api.cu", "qlb_tu_resident_f32.cu", "qlb_tu_stream_f32.cu", "qlb_tu_resident_f64.cu"]
+TRANSLATION_UNITS = ["qlb_api.cu", "qlb_tu_resident_f32.cu", "qlb_tu_stream.cu", "qlb_tu_resident_f64.cu"]
 
 
 def build_library(force: bool = False, verbose_ptxas: bool = True) -> Path:

@@ -29,7 +29,7 @@ EXPORTS = [
     "qlb_ctx_counters", "qlb_ctx_timer_start", "qlb_ctx_timer_stop",
     "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch", "qlb_sum_product_trace",
     "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device", "qlb_stats_allreduce",
-    "qlb_generate_batch_packed", "qlb_generate_device", "qlb_run_trials",
+    "qlb_generate_batch_packed", "qlb_generate_device", "qlb_run_trials", "qlb_test_f64_math",
 ]
 
 
@@ -47,6 +47,10 @@ class DecodeParams(C.Structure):
         ("enable_threshold", C.c_int32),
         ("flags", C.c_int32),
         ("threshold", C.c_double),
+        ("stream_max_bundles", C.c_int32),
+        ("stream_no_repack", C.c_int32),
+        ("block_threads", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -99,6 +103,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.qlb_generate_batch_packed.argtypes = [vp, i32, i64, vp, C.c_uint64, C.c_double, vp, vp, dp]
     lib.qlb_generate_device.argtypes = [vp, i32, i64, vp, C.c_uint64, C.c_double, vp, vp, dp]
     lib.qlb_run_trials.argtypes = [vp, vp, pp, i64, vp, C.c_uint64, C.c_double, vp, vp, dp]
+    lib.qlb_test_f64_math.argtypes = [vp, C.c_int, i64, vp, vp, vp]
     if path is None:
         _lib = lib
     return lib
@@ -117,14 +122,16 @@ def _ptr(a):
     return a.ctypes.data
 
 
-def make_params(precision=64, max_iterations=100, threshold=100.0, enable_threshold=True, fast_math=False, tier=None):
+def make_params(precision=64, max_iterations=100, threshold=100.0, enable_threshold=True, fast_math=False, tier=None,
+                stream_max_bundles=0, stream_no_repack=False, block_threads=0):
     if fast_math:  # the cheaper check rule of either precision
         flags = FLAG_F32_FAST_MATH if int(precision) == 32 else FLAG_F64_FUSED_RATIO
     else:
         flags = 0
     if tier is not None:
         flags |= (int(tier) + 1) << 8  # QLB_FLAG_TEST_TIER: force a slower storage tier
-    return DecodeParams(int(precision), int(max_iterations), int(bool(enable_threshold)), flags, float(threshold))
+    return DecodeParams(int(precision), int(max_iterations), int(bool(enable_threshold)), flags, float(threshold),
+                        int(stream_max_bundles), int(bool(stream_no_repack)), int(block_threads), 0)
 
 
 def pack_bits(bits, n=None) -> np.ndarray:
@@ -326,6 +333,14 @@ class Context:
         _check(self.lib, self.lib.qlb_run_trials(self.handle, code.handle, C.byref(params), seeds.size, _ptr(seeds), int(seed_offset),
                                                  float(qber), _ptr(it), _ptr(res), C.byref(exact)))
         return it, res, exact.value
+
+    def f64_math(self, op: int, a, b=None):
+        """Test probe: element-wise fp64 building blocks of the check rule (qlb_test_f64_math)."""
+        a = np.ascontiguousarray(a, np.float64)
+        b = None if b is None else np.ascontiguousarray(b, np.float64)
+        out = np.zeros_like(a)
+        _check(self.lib, self.lib.qlb_test_f64_math(self.handle, int(op), a.size, _ptr(a), _ptr(b), _ptr(out)))
+        return out
 
     def stats_allreduce(self, vectors, others=()):
         """In-process NCCL sum of uint64 statistics over this context and `others` (one vector per context)."""

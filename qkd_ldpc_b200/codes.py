@@ -208,3 +208,41 @@ def read_alist_fast(path) -> Matrix:
     row_ptr = np.zeros(m + 1, np.int32); row_ptr[1:] = np.cumsum(cw)
     regular = bool((bw == bw[0]).all() and (cw == cw[0]).all())
     return Matrix(n, m, row_ptr, col_idx.astype(np.int32), col_ptr, row_idx.astype(np.int32), regular, max_bw, max_cw, Path(path).name)
+
+
+def permutation_code(n: int, m: int, dv: int = 3, seed: int = 666) -> Matrix:
+    """A seeded column-weight-`dv` code from `dv` random permutations (Gallager's construction): layer l deals the bits, in
+    the order of a random permutation, round-robin to the checks (start offset l * m / dv), so every check gets floor or
+    ceil(n / m) bits per layer; a bit that drew the same check in two layers trades its entry with another bit's.
+    O(E) in numpy -- seconds at N = 1 000 000, where the PEG construction (host/peg.cpp) takes minutes -- for the large-frame
+    roofline and parity cases of BASELINE.json configs[3]. No girth conditioning: a throughput / parity workload, not a code
+    design. Adjacency lists sorted ascending, as in the shipped files."""
+    rng = np.random.default_rng(seed)
+    check_of = np.empty((dv, n), np.int64)
+    for layer in range(dv):
+        perm = rng.permutation(n)
+        check_of[layer, perm] = (np.arange(n) + layer * (m // dv)) % m
+    for _ in range(64):
+        clean = True
+        for hi in range(1, dv):
+            for lo in range(hi):
+                for b in np.flatnonzero(check_of[lo] == check_of[hi]):  # trade the later layer's entry with another bit's
+                    o = int(rng.integers(n))
+                    check_of[hi, b], check_of[hi, o] = check_of[hi, o], check_of[hi, b]
+                    clean = False
+        if clean:
+            break
+    else:
+        raise RuntimeError("permutation_code: could not remove the double edges")
+    row_idx = np.sort(check_of, axis=0).T.reshape(-1).astype(np.int32)  # bit-major, checks ascending
+    col_ptr = (np.arange(n + 1) * dv).astype(np.int32)
+    bits = np.repeat(np.arange(n, dtype=np.int64), dv)
+    order = np.lexsort((bits, row_idx))  # check-major, bits ascending inside a check
+    col_idx = bits[order].astype(np.int32)
+    cw = np.bincount(row_idx, minlength=m)
+    if (cw == 0).any():
+        raise RuntimeError("permutation_code: a check received no bit")
+    row_ptr = np.zeros(m + 1, np.int32)
+    row_ptr[1:] = np.cumsum(cw)
+    regular = bool((cw == cw[0]).all())
+    return Matrix(n, m, row_ptr, col_idx, col_ptr, row_idx, regular, dv, int(cw.max()), f"(N={n},M={m},CW={dv},SEED={seed},PERM)")

@@ -19,6 +19,29 @@
 
 using namespace qlb;
 
+namespace qlb
+{
+    // Test probe: the fp64 building blocks of the check rule, element-wise (see qlb_test_f64_math in the header).
+    __global__ void f64_math_probe_kernel(int op, long long n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out)
+    {
+        const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+            return;
+        const double x = a[i], y = b ? b[i] : 0.;
+        double r;
+        switch (op)
+        {
+        case 0: r = MathF64::quotient(x, y); break;
+        case 1: r = f64m::exp_neg(x); break;
+        case 2: r = f64m::log_ratio(x, y); break;
+        case 3: r = MathF64::tanh_half(x); break;
+        case 4: r = MathF64::two_atanh(x, y != 0.); break;
+        default: r = 0.; break;
+        }
+        out[i] = r;
+    }
+}
+
 namespace
 {
     thread_local std::string g_error;
@@ -134,6 +157,8 @@ namespace
             return fail(QLB_ERR_INVALID, "QLB_FLAG_F32_FAST_MATH requires fp32 precision");
         if ((p->flags & QLB_FLAG_F64_FUSED_RATIO) && p->precision != QLB_PRECISION_F64)
             return fail(QLB_ERR_INVALID, "QLB_FLAG_F64_FUSED_RATIO requires fp64 precision");
+        if (p->stream_max_bundles < 0 || p->block_threads < 0 || p->reserved != 0)
+            return fail(QLB_ERR_INVALID, "qlb_decode_params: negative execution knob or non-zero reserved field");
         return QLB_OK;
     }
 
@@ -158,9 +183,10 @@ namespace
             args.scratch = static_cast<unsigned char *>(ctx->scratch.p);
             args.scratch_stride = cv.total_scratch;
         }
-        if (std::getenv("QLB_DEBUG"))
+#ifdef QLB_DEBUG_LAUNCH
             std::fprintf(stderr, "[qlb] decode_kernel tier=%d reconcile=%d shapeW=%d threads=%d: %d CTA/SM, grid=%lld, smem=%zu B, scratch=%zu B/CTA\n",
                          kTier, (int)kReconcile, kShapeW, kThreads, per_sm, grid, cv.total_smem, cv.total_scratch);
+#endif
         QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;
@@ -216,6 +242,9 @@ namespace
         args.enable_thr = p->enable_threshold;
         args.thr = p->threshold;
         args.cap_f32 = p->enable_threshold ? (float)p->threshold : INFINITY;
+        args.stream_max_bundles = p->stream_max_bundles;
+        args.stream_no_repack = p->stream_no_repack;
+        args.block_threads = p->block_threads;
         const int forced = (p->flags >> 8) & 0xF ? ((p->flags >> 8) & 0xF) - 1 : -1; // bits 8..11: test hook, tier+1
         const bool fast = (p->flags & QLB_FLAG_F32_FAST_MATH) != 0;
         if (p->precision == QLB_PRECISION_F32 && forced < 0 && resident_f32_eligible(ctx, args.code))
@@ -749,6 +778,28 @@ extern "C"
         return QLB_OK;
     }
 
+    // ---- test probe of the fp64 building blocks -----------------------------------------------------------------------------
+    int qlb_test_f64_math(qlb_ctx *ctx, int op, int64_t n, const double *a, const double *b, double *out)
+    {
+        if (!ctx || n < 0 || op < 0 || op > 4 || (n > 0 && (!a || !out)))
+            return fail(QLB_ERR_INVALID, "qlb_test_f64_math: bad arguments");
+        if (n == 0)
+            return QLB_OK;
+        QLB_CUDA(cudaSetDevice(ctx->device));
+        const size_t bytes = (size_t)n * 8;
+        QLB_CUDA(ctx->in_llr.reserve(2 * bytes));
+        QLB_CUDA(ctx->scratch.reserve(bytes));
+        double *d_a = static_cast<double *>(ctx->in_llr.p), *d_b = b ? d_a + n : nullptr, *d_o = static_cast<double *>(ctx->scratch.p);
+        QLB_CUDA(cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (b)
+            QLB_CUDA(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        f64_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, n, d_a, d_b, d_o);
+        QLB_CUDA(cudaGetLastError());
+        QLB_CUDA(cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return QLB_OK;
+    }
+
     // ---- statistics all-reduce over the GPUs of this process (NCCL, loaded lazily) ---------------------------------------
     int qlb_stats_allreduce(qlb_ctx *const *ctxs, int n_ctx, uint64_t *const *vectors, size_t count)
     {
@@ -853,26 +904,41 @@ extern "C"
         if (!d_seeds || !d_alice_packed_out || !d_bob_packed_out)
             return fail(QLB_ERR_INVALID, "qlb_generate_device: null device buffer");
         QLB_CUDA(cudaSetDevice(ctx->device));
+        if (n_err > 0x7fffffffULL)
+            return fail(QLB_ERR_UNSUPPORTED, "qlb_generate_device: more than 2^31 - 1 flipped positions per key");
         const int words = (n_bits + 31) / 32;
-        const size_t pos_bytes = n_bits <= 65536 ? 2 : 4;
-        // bound the shuffle scratch: process the batch in slices
-        const int64_t slice = std::max<int64_t>(1, std::min<int64_t>(n_frames, (int64_t)((1ull << 30) / ((size_t)n_bits * pos_bytes))));
-        QLB_CUDA(ctx->gen_perm.reserve((size_t)slice * n_bits * pos_bytes));
-        for (int64_t f0 = 0; f0 < n_frames; f0 += slice)
+        const size_t pos_bytes = n_bits <= 65536 ? 2 : 4, state_bytes = n_err * pos_bytes; // per trial: the K-entry shuffle prefix
+        // Trials do not cooperate, so CTAs are small (64 or 32 threads) and the SM packs as many as its shared memory holds (each
+        // CTA also pays 1 KB of system shared memory); when not even one warp's prefixes fit they go to global memory.
+        const size_t smem_budget = (size_t)ctx->smem_optin - 1024;
+        int threads = 64;
+        if (threads * state_bytes > smem_budget)
+            threads = 32;
+        const bool shared = threads * state_bytes <= smem_budget;
+        if (!shared)
+            threads = 128;
+        const size_t smem = shared ? state_bytes * threads : 0;
+        int64_t slice = n_frames;
+        if (!shared)
         {
-            const int64_t nf = std::min(slice, n_frames - f0);
-            const unsigned grid = (unsigned)((nf + 127) / 128);
-            if (pos_bytes == 2)
-                generate_keys_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(nf, n_bits, words, (long long)n_err, d_seeds + f0, seed_offset,
-                                                                              (uint16_t *)ctx->gen_perm.p, d_alice_packed_out + f0 * words,
-                                                                              d_bob_packed_out + f0 * words);
-            else
-                generate_keys_kernel<uint32_t><<<grid, 128, 0, ctx->stream>>>(nf, n_bits, words, (long long)n_err, d_seeds + f0, seed_offset,
-                                                                              (uint32_t *)ctx->gen_perm.p, d_alice_packed_out + f0 * words,
-                                                                              d_bob_packed_out + f0 * words);
-            QLB_CUDA(cudaGetLastError());
+            slice = std::max<int64_t>(1, std::min<int64_t>(n_frames, (int64_t)((1ull << 30) / state_bytes))); // bound the scratch
+            QLB_CUDA(ctx->gen_perm.reserve((size_t)slice * state_bytes));
         }
-        return QLB_OK;
+        auto launch = [&](auto kern, auto *state) -> int
+        {
+            QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (int64_t f0 = 0; f0 < n_frames; f0 += slice)
+            {
+                const int64_t nf = std::min(slice, n_frames - f0);
+                kern<<<(unsigned)((nf + threads - 1) / threads), threads, smem, ctx->stream>>>(nf, n_bits, words, (int)n_err, d_seeds + f0, seed_offset, state,
+                                                                                                 d_alice_packed_out + f0 * words, d_bob_packed_out + f0 * words);
+                QLB_CUDA(cudaGetLastError());
+            }
+            return QLB_OK;
+        };
+        if (pos_bytes == 2)
+            return shared ? launch(generate_keys_kernel<uint16_t, true>, (uint16_t *)nullptr) : launch(generate_keys_kernel<uint16_t, false>, (uint16_t *)ctx->gen_perm.p);
+        return shared ? launch(generate_keys_kernel<uint32_t, true>, (uint32_t *)nullptr) : launch(generate_keys_kernel<uint32_t, false>, (uint32_t *)ctx->gen_perm.p);
     }
 
     int qlb_generate_batch_packed(qlb_ctx *ctx, int32_t n_bits, int64_t n_frames, const uint64_t *seeds, uint64_t seed_offset, double qber,

@@ -6,8 +6,10 @@
 // operand), have no branches, and are specialised to the argument ranges the decoder produces:
 //   exp_neg(x)   x in [-64, 0]           Cody-Waite reduction by ln 2 (round-to-nearest through the 1.5*2^52 shift), degree-13
 //                                        Taylor polynomial in Horner form, exponent insertion by integer add.  <= 1 ulp
-//   div_pos(a,d) d > 0, 2^-60 < d < 2^60 MUFU.RCP seed (fp32), one Newton step, one residual correction.       correctly rounded
-//                                        on every sampled input
+//   div_any(a,d) d normal, either sign    MUFU.RCP64H seed (rcp.approx.ftz.f64: ONE instruction on the double's high word, no
+//                                        fp64<->fp32 conversions), one Newton step, one residual correction: the quotient before
+//                                        its final rounding is within 2^-80 of a / d. d = 0 gives NaN for a = 0 (the reference's
+//                                        0/0) and for any other a (never asked); a subnormal d counts as 0 (ftz)
 //   log_pos(y)   y >= 2^-60, finite      the classical fdlibm scheme: y = 2^k m, m in [sqrt(1/2), sqrt 2), s = f/(2+f), f = m-1,
 //                                        log m = f - (f^2/2 - s (f^2/2 + R(s^2))), R = the degree-14 minimax polynomial
 //                                        Lg1..Lg7 of fdlibm's e_log.c (published algorithm and constants).     <= 1 ulp
@@ -43,22 +45,22 @@ namespace qlb
             return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
         }
 
-        // MUFU.RCP seed (relative error <= 2^-22) and ONE Newton step: y = (1/d)(1 + eps), |eps| <= 2^-44
-        __device__ __forceinline__ double rcp_pos(double d)
+        // MUFU.RCP64H seed (relative error ~2^-20) and ONE Newton step: y = (1/d)(1 + eps), |eps| <~ 2^-40. Either sign of d.
+        __device__ __forceinline__ double rcp_any(double d)
         {
-            float y0;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__double2float_rn(d)));
-            const double y = (double)y0;
-            return fma(y, fma(-d, y, 1.0), y);
+            double y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+            return fma(y0, fma(-d, y0, 1.0), y0);
         }
-        // q = a y is 44 bits good; the residual a - d q is exact in an FMA and |residual * y| carries a relative error of 2^-44
-        // again, so the corrected quotient is the rounding of a / d + O(2^-88): a second Newton step on y would buy nothing.
-        __device__ __forceinline__ double div_pos(double a, double d)
+        // q = a y is ~40 bits good; the residual a - d q is exact in an FMA and |residual * y| carries a relative error of 2^-40
+        // again, so the corrected quotient is the rounding of a / d (1 + O(2^-80)): a second Newton step on y would buy nothing.
+        __device__ __forceinline__ double div_any(double a, double d)
         {
-            const double y = rcp_pos(d);
+            const double y = rcp_any(d);
             const double q = a * y;
             return fma(fma(-d, q, a), y, q);
         }
+        __device__ __forceinline__ double div_pos(double a, double d) { return div_any(a, d); }
 
         __device__ __forceinline__ double log_pos(double y)
         {
@@ -102,24 +104,28 @@ namespace qlb
             return fma(dj, kLn2Hi, fma(2., s, fma(s, t2 + t1, dj * kLn2Lo)));
         }
 
-        // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped at 64 (the quotient is exactly +-1 far earlier)
+        // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped at 64 (the quotient is exactly +-1 far earlier).
+        // m = NaN comes back as +-1, NOT NaN: callers that can see a NaN message track it themselves (MathF64::check poisons the
+        // row product, TwoPass<MathF64>::t passes the NaN through) so that the hot loop pays one compare instead of a select pair.
         __device__ __forceinline__ double tanh_half(double m)
         {
-            const double e = exp_neg(-fmin(fabs(m), 64.));
-            return copysign(div_pos(1. - e, 1. + e), m);
+            const double a = fabs(m);
+            const double e = exp_neg(-(a < 64. ? a : 64.));
+            return copysign(div_any(1. - e, 1. + e), m);
         }
-        // 2 atanh(p) = ln((1 + p) / (1 - p)) with the IEEE outcomes of the literal expression at the edges:
-        // p = 1 -> +inf, p = -1 -> -inf, |p| > 1 or NaN -> NaN
-        __device__ __forceinline__ double two_atanh(double p)
+        // 2 atanh(p) = ln((1 + |p|) / (1 - |p|)) with p's sign, |p| <= 1 (the caller's p is a product of tanh values divided by one
+        // of its own factors, which cannot exceed 1 in magnitude: every partial product of factors <= 1 is <= each factor, and the
+        // quotient of a <= d rounds to <= 1). ONE division serves the ratio and the logarithm (log_ratio). Edges: |p| = 1 gives
+        // log_ratio(2, 0) = 1024 ln 2 -- finite, above any clamp the decoder can apply -- unless `want_inf`, the IEEE outcome +-inf
+        // of the literal expression (needed only when the clamp is off); p = NaN gives NaN through the arithmetic itself.
+        __device__ __forceinline__ double two_atanh(double p, bool want_inf)
         {
-            const double num = 1. + p, den = 1. - p;
-            const bool regular = num > 0. && den > 0.;
-            const double y = div_pos(regular ? num : 1., regular ? den : 1.);
-            double r = log_pos(y);
-            r = (den == 0. && num > 0.) ? __longlong_as_double(0x7ff0000000000000LL) : r;
-            r = (num == 0. && den > 0.) ? __longlong_as_double(0xfff0000000000000LL) : r;
-            r = (num < 0. || den < 0. || p != p) ? __longlong_as_double(0x7ff8000000000000LL) : r;
-            return r;
+            const double a = fabs(p);
+            const double den = 1. - a;
+            double r = log_ratio(1. + a, den);
+            if (want_inf)
+                r = den == 0. ? __longlong_as_double(0x7ff0000000000000LL) : r;
+            return copysign(r, p);
         }
     }
 }

@@ -75,6 +75,8 @@ namespace qlb
         unsigned long long *iter_total; // sum of executed iterations
         unsigned char *scratch;         // per-CTA global scratch (tiers 1, 2)
         size_t scratch_stride;
+        // host-side launch knobs (qlb_decode_params; not read by kernels)
+        int32_t stream_max_bundles, stream_no_repack, block_threads;
     };
 
     // ------------------------------------------------------------------------------------------------------------
@@ -101,42 +103,54 @@ namespace qlb
     struct MathF64
     {
         typedef double real;
-#if !defined(QLB_F64_LIBM_FORMS) && !defined(QLB_F64_LIBDEVICE_EXPLOG)
+#if !defined(QLB_F64_LIBM_FORMS)
         // tanh(m/2) = (1 - e^-|m|) / (1 + e^-|m|) and 2 atanh(p) = ln((1 + p) / (1 - p)): the same functions as the reference's
         // tanh(m / 2.) and 2. * atanh(p), evaluated branch-free with the constant-memory exp / log / divide of qlb_f64_math.cuh
         // (libdevice's tanh/atanh take divergent small/large-argument paths, and 70 % of what its exp/log/divide issue is
         // constant and register shuffling). They differ from glibc's results at the ulp level, as libdevice's own do; what is
-        // contractual is the per-frame outcome, checked on 9 216 + 10 240 reference frames (profiles/parity_r01.md,
-        // multirate_r01.md). -DQLB_F64_LIBDEVICE_EXPLOG keeps the forms but calls libdevice exp/log and operator/;
-        // -DQLB_F64_LIBM_FORMS restores the literal tanh / atanh calls.
+        // contractual is the per-frame outcome, checked against the reference's own outcomes on the campaign fixture
+        // (tests/golden/campaign_n10240.npz, 49 152 frames). -DQLB_F64_LIBM_FORMS restores the literal tanh / atanh calls.
+        //
+        // NaN (0/0 of an exactly-zero message, or inf - inf with the clamp off): the reference's tanh(NaN) = NaN poisons the row
+        // product, so EVERY output of the check is NaN (:231-243). f64m::tanh_half does not propagate NaN by itself; the rule
+        // tracks it with one compare per edge and poisons the product once per check.
+        static constexpr bool kOwnForms = true;
         static __device__ __forceinline__ double tanh_half(double m) { return f64m::tanh_half(m); }
-        static __device__ __forceinline__ double two_atanh(double p) { return f64m::two_atanh(p); }
-#elif defined(QLB_F64_LIBDEVICE_EXPLOG)
-        static __device__ __forceinline__ double tanh_half(double m)
-        {
-            const double e = exp(-fmin(fabs(m), 64.));
-            return copysign((1. - e) / (1. + e), m);
-        }
-        static __device__ __forceinline__ double two_atanh(double p) { return log((1. + p) / (1. - p)); }
+        // |out| before the clamp; want_inf: the clamp is off, a saturated product must give inf (see f64m::two_atanh)
+        static __device__ __forceinline__ double two_atanh(double p, bool want_inf) { return f64m::two_atanh(p, want_inf); }
 #else
+        static constexpr bool kOwnForms = false;
         static __device__ __forceinline__ double tanh_half(double m) { return tanh(m / 2.); }
-        static __device__ __forceinline__ double two_atanh(double p) { return 2. * atanh(p); }
+        static __device__ __forceinline__ double two_atanh(double p, bool) { return 2. * atanh(p); }
 #endif
+        static __device__ __forceinline__ double quotient(double a, double d)
+        {
+#if !defined(QLB_F64_LIBM_FORMS)
+            return f64m::div_any(a, d);
+#else
+            return a / d;
+#endif
+        }
         template <int W>
         static __device__ __forceinline__ void check(double (&v)[W], int w, bool s, bool en, double thr)
         {
             double row = s ? -1. : 1.;
+            bool poisoned = false;
 #pragma unroll
             for (int k = 0; k < W; ++k)
                 if (k < w)
                 {
+                    if (kOwnForms)
+                        poisoned |= v[k] != v[k];
                     v[k] = tanh_half(v[k]);
                     row *= v[k];
                 }
+            if (kOwnForms)
+                row = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : row;
 #pragma unroll
             for (int k = 0; k < W; ++k)
                 if (k < w)
-                    v[k] = clamp_msg(two_atanh(row / v[k]), thr, en);
+                    v[k] = clamp_msg(two_atanh(quotient(row, v[k]), !en), thr, en);
         }
     };
 
@@ -277,8 +291,13 @@ namespace qlb
     struct TwoPass<MathF64>
     {
         static constexpr bool kZeroAware = false; // the reference divides, 0/0 included
-        static __device__ __forceinline__ double t(double m) { return MathF64::tanh_half(m); }
-        static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(MathF64::two_atanh(p), thr, en); }
+        static __device__ __forceinline__ double t(double m)
+        {
+            const double r = MathF64::tanh_half(m);
+            return (MathF64::kOwnForms && m != m) ? m : r; // tanh(NaN) = NaN (stored, then multiplied into the row product)
+        }
+        static __device__ __forceinline__ double quotient(double a, double d) { return MathF64::quotient(a, d); }
+        static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(MathF64::two_atanh(p, !en), thr, en); }
     };
     template <>
     struct TwoPass<MathF64Fused> : TwoPass<MathF64> // checks wider than the unrolled shapes keep the literal order
@@ -289,6 +308,7 @@ namespace qlb
     {
         static constexpr bool kZeroAware = true;
         static __device__ __forceinline__ float t(float m) { return tanhf(0.5f * m); }
+        static __device__ __forceinline__ float quotient(float a, float d) { return a / d; }
         static __device__ __forceinline__ float out(float p, bool en, float thr) { return clamp_msg(2.f * atanhf(p), thr, en); }
     };
     template <>
@@ -300,6 +320,7 @@ namespace qlb
             const float e = exp2f(-1.4426950408889634f * fabsf(m));
             return copysignf(__fdividef(1.f - e, 1.f + e), m);
         }
+        static __device__ __forceinline__ float quotient(float a, float d) { return a / d; }
         static __device__ __forceinline__ float out(float p, bool en, float thr)
         {
             const float ap = fabsf(p);
@@ -553,9 +574,9 @@ namespace qlb
                                 const Real t = msg[code.base[k] + p];
                                 Real prod;
                                 if (!TP::kZeroAware)
-                                    prod = row / t;
+                                    prod = TP::quotient(row, t);
                                 else if (zeros == 0)
-                                    prod = row / t;
+                                    prod = TP::quotient(row, t);
                                 else if (zeros == 1)
                                     prod = (t == (Real)0) ? row : (Real)0;
                                 else

@@ -57,7 +57,7 @@ namespace qlb
             const int32_t groups = warps * max_bit_w;
             // Only codes that can live in shared memory profit (slots < 65535 is the resident kernels' limit); for larger codes
             // the natural order keeps the first edges of consecutive bits on consecutive message rows (DRAM locality).
-            if (m < 64 || groups <= 0 || e >= 65535 || std::getenv("QLB_NO_BANK_SPREAD"))
+            if (m < 64 || groups <= 0 || e >= 65535)
                 return;
             // groups a check belongs to (one per edge): (warp of the bit, position of this edge in the bit's list)
             std::vector<std::vector<int32_t>> groups_of(m);
@@ -88,23 +88,6 @@ namespace qlb
                         tot += mx;
                         ++used;
                     }
-                }
-                if (std::getenv("QLB_BANK_DEBUG"))
-                {
-                    long hist[8] = {0}, pairs = 0;
-                    for (int32_t g = 0; g < groups; ++g)
-                    {
-                        int mx = 0;
-                        for (int b = 0; b < 32; ++b)
-                        {
-                            const int v = c[static_cast<size_t>(g) * 32 + b];
-                            mx = std::max(mx, v);
-                            pairs += v * (v - 1) / 2;
-                        }
-                        ++hist[std::min(mx, 7)];
-                    }
-                    std::fprintf(stderr, "bank placement: groups by max multiplicity 1:%ld 2:%ld 3:%ld 4:%ld 5+:%ld colliding pairs %ld\n",
-                                 hist[1], hist[2], hist[3], hist[4], hist[5] + hist[6] + hist[7], pairs);
                 }
                 return used ? tot / static_cast<double>(used) : 0.0;
             };
@@ -182,8 +165,7 @@ namespace qlb
                         }
                         bank[j] = to;
                     };
-                    const char *env = std::getenv("QLB_BANK_TRIALS");
-                    const size_t trials = sz * (env ? std::strtoul(env, nullptr, 10) : 400);
+                    const size_t trials = sz * 400;
                     for (size_t t = 0; t < trials; ++t)
                     {
                         const int32_t j1 = members[next() % sz], j2 = members[next() % sz];

@@ -3,13 +3,20 @@
 //
 // 30 720 doubles (240 KB) do not fit in the 227 KB of shared memory of one SM, so the message array is SPLIT: the first
 // `smem_slots` physical slots (~92 % on the N=10240 code: all of edge positions 0..4 and the head of position 5) live in
-// shared memory, the tail in a small per-CTA global scratch (coalesced in the check pass, L2 hits in the bit pass). To
-// make room, the slot table and the bit index of every slot are streamed from global memory (read-only, coalesced, shared
-// by all CTAs through L2), and the hard decisions are kept bit-packed (the bit pass ballots them into the key words); the
-// parity of a check is formed from those packed decisions through the slot->bit table at the start of the NEXT check pass
-// (bit-exact fp64 messages leave no spare mantissa bit to carry the decision as the fp32 kernel does). Iteration counts,
-// flags and keys follow the reference's definitions exactly (src/qkd_ldpc_algorithm.cpp:175-345, 398-447); the generic
-// decode_kernel<MathF64> stays as the fallback for codes this kernel does not take.
+// shared memory, the tail in a small per-CTA global scratch (coalesced in the check pass, L2 hits in the bit pass). The
+// host cuts the walk over the sorted checks into segments (SegTable64) inside which the split falls the same way for every
+// check -- all rows in shared memory, or exactly the last row in the tail -- so the hot loops address their messages
+// without a per-access test.
+//
+// Convergence (calculate_syndrome + arrays_equal after every bit pass, src/qkd_ldpc_algorithm.cpp:277-298) is tracked
+// INCREMENTALLY, in integers, exactly: s_unsat holds one bit per check, syndrome(z) ^ target. It is initialised once per
+// frame from the hard decision of the priors (a walk over the slot->bit table), and from then on a bit whose decision
+// flips in a bit pass toggles the bits of its checks (a few hundred shared-memory atomics in the first rounds, a handful
+// later, against a 30 720-edge gather per round before). The frame has converged when the words are all zero -- known right
+// after the bit pass, so a converged frame no longer pays a speculative check pass, and the check pass itself carries
+// nothing but the check rule (bit-exact fp64 messages leave no spare mantissa bit to carry the decision as the fp32 kernel
+// does). Iteration counts, flags and keys follow the reference's definitions exactly (src/qkd_ldpc_algorithm.cpp:175-345,
+// 398-447); the generic decode_kernel<MathF64> stays as the fallback for codes this kernel does not take.
 #pragma once
 #include "qlb_resident_f32.cuh"
 
@@ -17,11 +24,26 @@ namespace qlb
 {
     constexpr int kResident64Threads = 768; // launch bound; the host picks the block size that balances the node walks
     constexpr size_t kResident64StaticSmem = 2 * kResident64Threads * 4 + 1024;
+    constexpr int kResident64MaxSegs = 24;
+    constexpr int kResident64FastW = 8; // weights up to this get the split-specialised loops
+
+    // One run of sorted check positions [lo, hi): weight exactly w; `tail` rows (edge positions w - tail .. w - 1) live in the
+    // global tail for every check of the run (0 or 1), or tail = -1: decide per access.
+    struct Seg64
+    {
+        uint32_t lo, hi;
+        int32_t w, tail;
+    };
+    struct SegTable64
+    {
+        int32_t n;
+        Seg64 seg[kResident64MaxSegs];
+    };
 
     struct Split64
     {
         double *smem;
-        double *gmem;
+        double *gmem; // slot s >= smem_slots is gmem[s - smem_slots]
         uint32_t smem_slots;
         __device__ __forceinline__ double ld(uint32_t slot) const { return slot < smem_slots ? smem[slot] : gmem[slot - smem_slots]; }
         __device__ __forceinline__ void st(uint32_t slot, double v) const
@@ -36,11 +58,9 @@ namespace qlb
     __host__ __device__ inline size_t resident64_small_bytes(int n, int m)
     {
         const size_t wn = align_up((size_t)(n + 31) / 32 * 4, 16), wm = align_up((size_t)(m + 31) / 32 * 4, 16);
-        return 3 * wn + wm;
+        return 3 * wn + 2 * wm; // Bob, Alice, decisions | syndrome (natural order), unsatisfied checks (sorted order)
     }
 
-    // All checks of weight exactly W in [lo, hi). zsrc: packed bits whose parity per check is wanted (the last hard decision,
-    // or Alice's key during the first pass, which yields her syndrome: src/qkd_ldpc_algorithm.cpp:413-414).
     struct Base64FromParams
     {
         const DecodeArgs &args;
@@ -52,74 +72,72 @@ namespace qlb
         __device__ __forceinline__ uint32_t operator()(int k) const { return base[k]; }
     };
 
-    template <typename Math, int W, typename Base>
-    __device__ __forceinline__ uint32_t check_segment64(int kThreads, const Split64 &msg, const Base base, const uint16_t *__restrict__ col_of_slot,
-                                                        const uint32_t *__restrict__ zsrc, uint32_t lo, uint32_t hi, uint32_t &my_syn, int &rbit,
-                                                        bool first, bool en, double thr)
+    // The check rule (:220-249) on all checks of one segment. kTail as Seg64::tail.
+    template <typename Math, int W, int kTail, typename Base>
+    __device__ __forceinline__ void check_segment64(int kThreads, const Split64 &msg, const Base base, uint32_t lo, uint32_t hi, uint32_t my_syn,
+                                                    int &rbit, bool en, double thr)
     {
-        uint32_t bad = 0;
+        double *gm = msg.gmem - msg.smem_slots;
 #pragma unroll 1
         for (uint32_t p = lo + threadIdx.x; p < hi; p += kThreads, ++rbit)
         {
             double v[W];
-            uint32_t par = 0;
 #pragma unroll
             for (int k = 0; k < W; ++k)
             {
                 const uint32_t slot = base(k) + p;
-                const uint32_t col = col_of_slot[slot];
-                par ^= zsrc[col >> 5] >> (col & 31);
-                v[k] = msg.ld(slot);
+                v[k] = kTail < 0 ? msg.ld(slot) : (k < W - kTail ? msg.smem[slot] : gm[slot]);
             }
-            par &= 1u;
-            uint32_t sb;
-            if (first)
-            {
-                sb = par;
-                my_syn |= sb << rbit;
-            }
-            else
-            {
-                sb = (my_syn >> rbit) & 1u;
-                bad |= par ^ sb; // calculate_syndrome + arrays_equal of :277-298, one iteration late
-            }
-            Math::template check<W>(v, W, sb != 0, en, thr);
+            Math::template check<W>(v, W, ((my_syn >> rbit) & 1u) != 0, en, thr);
 #pragma unroll
             for (int k = 0; k < W; ++k)
-                msg.st(base(k) + p, v[k]);
+            {
+                const uint32_t slot = base(k) + p;
+                if (kTail < 0)
+                    msg.st(slot, v[k]);
+                else if (k < W - kTail)
+                    msg.smem[slot] = v[k];
+                else
+                    gm[slot] = v[k];
+            }
         }
-        return bad;
     }
 
     // Weights 9..16 (the R >= 0.7 codes of the CW = 3 family) are kept out of line: their register appetite (2 x W doubles live) must
     // not leak into the hot instantiations; some spilling inside them is still far cheaper than the generic kernel's L2 round trips.
-    // Returns {bit 0: parity failure, bits 1..: advanced round counter} and the (first pass) accumulated syndrome bits.
     template <typename Math, int W>
-    __device__ __noinline__ uint2 check_segment64_wide(int kThreads, const Split64 msg, const uint32_t *s_base, const uint16_t *col_of_slot,
-                                                       const uint32_t *zsrc, uint32_t lo, uint32_t hi, uint32_t my_syn, int rbit, bool first, bool en,
-                                                       double thr)
+    __device__ __noinline__ int check_segment64_wide(int kThreads, const Split64 msg, const uint32_t *s_base, uint32_t lo, uint32_t hi, uint32_t my_syn,
+                                                     int rbit, bool en, double thr)
     {
-        const uint32_t bad = check_segment64<Math, W>(kThreads, msg, Base64FromSmem{s_base}, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr);
-        return make_uint2((bad & 1u) | ((uint32_t)rbit << 1), my_syn);
+        check_segment64<Math, W, -1>(kThreads, msg, Base64FromSmem{s_base}, lo, hi, my_syn, rbit, en, thr);
+        return rbit;
     }
 
-    // kBW: uniform bit weight. Host-checked: slots < 65535, n < 65536, max_check_w <= 16, n % 32 == 0, n, m <= 32 * kThreads.
+    // Sorted position of the check that owns `slot` (rows are laid out one edge position after the other, qlb_layout.hpp).
+    static __device__ __noinline__ uint32_t check_of_slot64(uint32_t slot, const uint32_t *s_base, int max_cw)
+    {
+        int k = max_cw - 1;
+        while (k > 0 && slot < s_base[k])
+            --k;
+        return slot - s_base[k];
+    }
+
+    // kBW: uniform bit weight. Host-checked: slots < 65535, n < 65536, max_check_w <= 16, n % 32 == 0, and every thread's walk over
+    // the segments / the bits stays within 32 rounds (one register bit per node a thread visits).
     template <typename Math, bool kReconcile, int kBW, int kMaxThreads>
-    __global__ void __launch_bounds__(kMaxThreads, 1) decode_resident_f64_kernel(const DecodeArgs args, uint32_t smem_slots,
+    __global__ void __launch_bounds__(kMaxThreads, 1) decode_resident_f64_kernel(const DecodeArgs args, const SegTable64 segs, uint32_t smem_slots,
                                                                                  const uint16_t *__restrict__ col_of_slot)
     {
         const int kThreads = blockDim.x; // multiple of 32, <= kMaxThreads
         extern __shared__ __align__(16) unsigned char smem[];
-        __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
         __shared__ uint32_t s_park_bob[kMaxThreads], s_park_syn[kMaxThreads];
         __shared__ uint32_t s_base[kResidentMaxCW];
-        __shared__ int s_nseg;
         __shared__ long long s_frame;
 
         const CodeDev &code = args.code;
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31;
         const int words_n = code.words_n, words_m = code.words_m;
-        const size_t wn = align_up((size_t)words_n * 4, 16);
+        const size_t wn = align_up((size_t)words_n * 4, 16), wm = align_up((size_t)words_m * 4, 16);
         if (tid < kResidentMaxCW)
             s_base[tid] = code.base[tid];
 
@@ -132,26 +150,9 @@ namespace qlb
         uint32_t *s_alice = reinterpret_cast<uint32_t *>(tail + wn);
         uint32_t *s_z = reinterpret_cast<uint32_t *>(tail + 2 * wn);
         uint32_t *s_synn = reinterpret_cast<uint32_t *>(tail + 3 * wn);
+        uint32_t *s_unsat = reinterpret_cast<uint32_t *>(tail + 3 * wn + wm);
         const uint16_t *bslot = code.bit_slots16;
-
-        if (tid == 0)
-        {
-            int ns = 0;
-            for (int w = code.max_check_w; w >= 0; --w)
-            {
-                const uint32_t lo = (w < code.max_check_w) ? code.cnt[w] : 0u, hi = (w > 0) ? code.cnt[w - 1] : (uint32_t)m;
-                if (lo < hi)
-                {
-                    s_seg_w[ns] = (uint32_t)w;
-                    s_seg_lo[ns] = lo;
-                    s_seg_hi[ns] = hi;
-                    ++ns;
-                }
-            }
-            s_nseg = ns;
-        }
-        __syncthreads();
-        const int nseg = s_nseg;
+        const int nseg = segs.n;
         const bool en = args.enable_thr != 0;
         const double thr = args.thr;
 
@@ -184,9 +185,12 @@ namespace qlb
                 for (int w = tid; w < words_m; w += kThreads)
                     s_synn[w] = args.syndrome_in[f * words_m + w];
             }
+            for (int w = tid; w < words_m; w += kThreads)
+                s_unsat[w] = 0;
             __syncthreads();
 
-            // messages <- priors, unclamped (:182-190); Bob's bit of the r-th bit this thread visits -> bit r
+            // messages <- priors, unclamped (:182-190); z0 = the priors' own hard decision (the base of the incremental
+            // syndrome); Bob's bit of the r-th bit this thread visits -> bit r of s_park_bob
             {
                 uint32_t my_bob = 0;
                 int r = 0;
@@ -204,113 +208,93 @@ namespace qlb
 #pragma unroll
                     for (int a = 0; a < kBW; ++a)
                         msg.st(bslot[a * n + i], prior);
+                    const uint32_t word = __ballot_sync(0xffffffffu, prior <= 0.); // n % 32 == 0: whole warps only
+                    if (lane == 0)
+                        s_z[i >> 5] = word;
                 }
                 s_park_bob[tid] = my_bob;
             }
-            if (!kReconcile)
+            __syncthreads();
+
+            // One walk over this thread's checks through the slot -> bit table: the target syndrome bit of its r-th check -> bit
+            // r of my_syn (reconcile mode: Alice's syndrome, :413-414), and s_unsat <- syndrome(z0) ^ target.
             {
-                // target syndrome bits of this thread's checks, in its walk order
                 uint32_t my_syn = 0;
                 int r = 0;
                 for (int sg = 0; sg < nseg; ++sg)
-                    for (uint32_t p = s_seg_lo[sg] + tid; p < s_seg_hi[sg]; p += kThreads, ++r)
-                    {
-                        const uint32_t j = code.check_order[p];
-                        my_syn |= ((s_synn[j >> 5] >> (j & 31)) & 1u) << r;
-                    }
-                s_park_syn[tid] = my_syn;
-            }
-            __syncthreads();
-
-            // `it` counts completed bit passes; the check pass of round it > 0 first evaluates the parity of bit pass `it`
-            // As in the fp32 kernel: when the previous check pass saw only a handful of unsatisfied checks, look at the parity on its
-            // own before paying a whole check pass (85 % of an fp64 iteration) to find out that the frame has converged.
-            int it = 0;
-            bool success = false, quiet = false;
-            for (;;)
-            {
-                if (quiet && it > 0)
                 {
-                    uint32_t wrong = 0;
-                    const uint32_t my_syn = s_park_syn[tid];
-                    int r = 0;
-                    for (int sg = 0; sg < nseg; ++sg)
+                    const int w = segs.seg[sg].w;
+                    for (uint32_t p = segs.seg[sg].lo + tid; p < segs.seg[sg].hi; p += kThreads, ++r)
                     {
-                        const int w = (int)s_seg_w[sg];
-                        for (uint32_t p = s_seg_lo[sg] + tid; p < s_seg_hi[sg]; p += kThreads, ++r)
+                        uint32_t pa = 0, pz = 0;
+                        for (int k = 0; k < w; ++k)
                         {
-                            uint32_t x = my_syn >> r;
-                            for (int k = 0; k < w; ++k)
-                            {
-                                const uint32_t col = col_of_slot[code.base[k] + p];
-                                x ^= s_z[col >> 5] >> (col & 31);
-                            }
-                            wrong |= x;
+                            const uint32_t col = col_of_slot[s_base[k] + p];
+                            pz ^= s_z[col >> 5] >> (col & 31);
+                            if (kReconcile)
+                                pa ^= s_alice[col >> 5] >> (col & 31);
                         }
-                    }
-                    if (!__syncthreads_or((int)(wrong & 1u)))
-                    {
-                        success = true; // :285-298
-                        break;
+                        const uint32_t j = code.check_order[p];
+                        uint32_t sb;
+                        if (kReconcile)
+                        {
+                            sb = pa & 1u;
+                            if (sb && args.syndrome_out)
+                                atomicOr(&s_synn[j >> 5], 1u << (j & 31));
+                        }
+                        else
+                            sb = (s_synn[j >> 5] >> (j & 31)) & 1u;
+                        my_syn |= sb << r;
+                        if ((sb ^ pz) & 1u)
+                            atomicOr(&s_unsat[p >> 5], 1u << (p & 31));
                     }
                 }
-                const bool first = kReconcile && it == 0;
-                uint32_t bad = 0;
+                s_park_syn[tid] = my_syn;
+            }
+            // (no barrier needed before the first check pass: it touches messages only; s_unsat is next touched after two barriers)
+
+            int it = 0; // completed bit passes
+            bool success = false;
+            while (it < args.max_it)
+            {
+                // check pass (:220-249)
                 {
-                    uint32_t my_syn = first ? 0u : s_park_syn[tid];
-                    const uint32_t *zsrc = first ? s_alice : s_z;
+                    const uint32_t my_syn = s_park_syn[tid];
                     int rbit = 0;
 #pragma unroll 1
                     for (int sg = 0; sg < nseg; ++sg)
                     {
-                        const uint32_t lo = s_seg_lo[sg], hi = s_seg_hi[sg];
-                        switch (s_seg_w[sg])
+                        const uint32_t lo = segs.seg[sg].lo, hi = segs.seg[sg].hi;
+                        switch (segs.seg[sg].w * 4 + (segs.seg[sg].tail & 3))
                         {
-#define QLB_SEG64(W_) case W_: bad |= check_segment64<Math, W_>(kThreads, msg, Base64FromParams{args}, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); break;
-#define QLB_SEG64W(W_) case W_: { const uint2 rv = check_segment64_wide<Math, W_>(kThreads, msg, s_base, col_of_slot, zsrc, lo, hi, my_syn, rbit, first, en, thr); \
-                                  bad |= rv.x & 1u; rbit = (int)(rv.x >> 1); my_syn = rv.y; } break;
+#define QLB_SEG64(W_)                                                                                                                     \
+    case W_ * 4 + 0: check_segment64<Math, W_, 0>(kThreads, msg, Base64FromParams{args}, lo, hi, my_syn, rbit, en, thr); break;          \
+    case W_ * 4 + 1: check_segment64<Math, W_, 1>(kThreads, msg, Base64FromParams{args}, lo, hi, my_syn, rbit, en, thr); break;          \
+    case W_ * 4 + 3: check_segment64<Math, W_, -1>(kThreads, msg, Base64FromParams{args}, lo, hi, my_syn, rbit, en, thr); break;
+#define QLB_SEG64W(W_) \
+    case W_ * 4 + 3: rbit = check_segment64_wide<Math, W_>(kThreads, msg, s_base, lo, hi, my_syn, rbit, en, thr); break;
                             QLB_SEG64(1) QLB_SEG64(2) QLB_SEG64(3) QLB_SEG64(4) QLB_SEG64(5) QLB_SEG64(6) QLB_SEG64(7) QLB_SEG64(8)
                             QLB_SEG64W(9) QLB_SEG64W(10) QLB_SEG64W(11) QLB_SEG64W(12) QLB_SEG64W(13) QLB_SEG64W(14) QLB_SEG64W(15) QLB_SEG64W(16)
 #undef QLB_SEG64
 #undef QLB_SEG64W
-                        default: // checks without edges: satisfied only by a zero syndrome bit
-                            for (uint32_t p = lo + tid; p < hi; p += kThreads, ++rbit)
-                                if (!first)
-                                    bad |= (my_syn >> rbit) & 1u;
+                        default: // checks without edges send nothing
+                            for (uint32_t p = lo + tid; p < hi; p += kThreads)
+                                ++rbit;
                             break;
                         }
                     }
-                    if (first)
-                    {
-                        s_park_syn[tid] = my_syn;
-                        if (args.syndrome_out)
-                        {
-                            int r = 0;
-                            for (int sg = 0; sg < nseg; ++sg)
-                                for (uint32_t p = s_seg_lo[sg] + tid; p < s_seg_hi[sg]; p += kThreads, ++r)
-                                    if ((my_syn >> r) & 1u)
-                                    {
-                                        const uint32_t j = code.check_order[p];
-                                        atomicOr(&s_synn[j >> 5], 1u << (j & 31));
-                                    }
-                        }
-                    }
                 }
-                const int any_bad = __syncthreads_count((int)(bad & 1u)); // threads with an unsatisfied check
-                if (it > 0 && !any_bad)
-                {
-                    success = true; // :285-298
-                    break;
-                }
-                quiet = it > 0 && any_bad <= kQuietChecks;
-                if (it == args.max_it)
-                    break; // :337-344
-                // bit pass: total (:256-258), decision (:259-266), extrinsic + clamp (:300-316)
+                __syncthreads();
+                // bit pass: total (:256-258), decision (:259-266), extrinsic + clamp (:300-316); a flipped decision toggles the
+                // unsatisfied-bits of the bit's checks
                 {
                     uint32_t my_bob = s_park_bob[tid];
                     const uint16_t *bs = bslot + tid;
                     uint32_t *zw = s_z + (tid >> 5);
-
+                    uint32_t nx[kBW];
+#pragma unroll
+                    for (int a = 0; a < kBW; ++a)
+                        nx[a] = tid < n ? bs[a * n] : 0;
 #pragma unroll 1
                     for (int i = tid; i < n; i += kThreads)
                     {
@@ -326,7 +310,12 @@ namespace qlb
                         double c[kBW];
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
-                            sl[a] = bs[a * n];
+                            sl[a] = nx[a];
+                        bs += kThreads;
+                        if (i + kThreads < n) // next round's slot indices (L2) while this round's messages are gathered
+#pragma unroll
+                            for (int a = 0; a < kBW; ++a)
+                                nx[a] = bs[a * n];
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
                             c[a] = msg.ld(sl[a]);
@@ -339,14 +328,31 @@ namespace qlb
                         for (int a = 0; a < kBW; ++a)
                             msg.st(sl[a], clamp_msg(total - c[a], thr, en));
                         const uint32_t word = __ballot_sync(0xffffffffu, z);
+                        const uint32_t flips = word ^ *zw;
+                        if ((flips >> lane) & 1u)
+#pragma unroll 1
+                            for (int a = 0; a < kBW; ++a)
+                            {
+                                const uint32_t p = check_of_slot64(sl[a], s_base, code.max_check_w);
+                                atomicXor(&s_unsat[p >> 5], 1u << (p & 31));
+                            }
+                        __syncwarp();
                         if (lane == 0)
                             *zw = word;
-                        bs += kThreads;
                         zw += kThreads / 32;
                     }
                 }
                 ++it;
                 __syncthreads();
+                // calculate_syndrome + arrays_equal of :277-298: all checks satisfied?
+                int open = 0;
+                for (int w = tid; w < words_m; w += kThreads)
+                    open |= s_unsat[w] != 0u;
+                if (!__syncthreads_or(open))
+                {
+                    success = true; // :285-298
+                    break;
+                }
             }
 
             int differs = 0;
@@ -367,7 +373,7 @@ namespace qlb
                 uint8_t r = success ? 1 : 0;
                 if (kReconcile && !any_diff)
                     r |= 2;
-                args.iterations[f] = (uint32_t)it;
+                args.iterations[f] = (uint32_t)it; // == max_it on failure (:344)
                 args.result[f] = r;
                 atomicAdd(args.iter_total, (unsigned long long)it);
             }

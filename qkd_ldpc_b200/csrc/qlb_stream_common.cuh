@@ -1,0 +1,185 @@
+// Shared pieces of the fp32 frame-interleaved "streaming" decoder (qlb_stream_split.cuh): the kernels for codes whose
+// messages do not fit in shared memory (BASELINE.json configs[3]: N = 100 000 ... 1 000 000) -- the HBM-bound design point
+// of SURVEY.md 8d.
+//
+// Frames are decoded in GROUPS of G = 32 * VEC (VEC = 4: 128-bit accesses). Messages are stored slot-major, frame-minor:
+// msg[slot][G]. A WARP works on one node at a time and lane l owns frames VEC*l ... VEC*l+VEC-1 of the group, so whatever
+// the Tanner graph looks like, every message access of the warp is one fully coalesced row of G floats (512 B for VEC = 4),
+// and the graph indices are warp-uniform (one broadcast load per node, amortised over the G frames). Traffic per executed
+// iteration is the algorithmic 16 B per edge and frame (read + write in the check pass, read + write in the bit pass) plus
+// < 2 % of indices and packed bits. Keys, decisions and syndromes are kept bit-transposed per group ([node][VEC] words, word j
+// bit l = frame VEC*l + j) so a lane extracts its frames' bits with one shift; the transposes run once per group with
+// __ballot_sync. Node arithmetic, the decision-in-LSB trick and the convergence rule are those of the SM-resident kernel
+// (qlb_resident_f32.cuh); a converged frame is frozen (decisions and counters kept) while its group finishes.
+#pragma once
+#include "qlb_resident_f32.cuh"
+
+namespace qlb
+{
+
+    template <int VEC>
+    struct VecIO;
+    template <>
+    struct VecIO<4>
+    {
+        static __device__ __forceinline__ void load(const float *p, float (&v)[4])
+        {
+#ifdef QLB_STREAM_CS
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
+#else
+            const float4 t = *reinterpret_cast<const float4 *>(p);
+#endif
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+        static __device__ __forceinline__ void store(float *p, const float (&v)[4])
+        {
+#ifdef QLB_STREAM_CS
+            __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+#else
+            *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+#endif
+        }
+    };
+    template <>
+    struct VecIO<1>
+    {
+        static __device__ __forceinline__ void load(const float *p, float (&v)[1]) { v[0] = *p; }
+        static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
+    };
+
+    // Software prefetch into L2: registers bound how many demand loads a warp can keep in flight (W rows of 512 B), which is
+    // not enough to cover HBM latency at 16 warps per SM; prefetching the NEXT node's rows costs no registers and turns the
+    // demand loads that follow into L2 hits.
+    __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+    // per-group scratch carve-up (bytes); G = 32 * VEC
+    struct StreamCarve
+    {
+        size_t msg, bobT, aliceT, zT, synT, total;
+    };
+    __host__ __device__ inline StreamCarve stream_carve(int n, int m, int slots, int vec)
+    {
+        StreamCarve c{};
+        const size_t G = 32 * (size_t)vec;
+        size_t o = 0;
+        c.msg = o; o += align_up((size_t)slots * G * 4, 256);
+        c.bobT = o; o += align_up((size_t)n * vec * 4, 256);
+        c.aliceT = o; o += align_up((size_t)n * vec * 4, 256);
+        c.zT = o; o += align_up((size_t)n * vec * 4, 256);
+        c.synT = o; o += align_up((size_t)m * vec * 4, 256);
+        c.total = o;
+        return c;
+    }
+
+    // One check of weight exactly W for the VEC frames of this lane.
+    // row_stride: floats between the rows of consecutive slots (G, or B * G when B groups are interleaved slot by slot)
+    template <typename Rule, int W, int VEC>
+    __device__ __forceinline__ void stream_check(float *__restrict__ msg, const CodeDev &code, uint32_t p, int lane, uint32_t *__restrict__ synT,
+                                                 float cap, bool first, uint32_t (&bad)[VEC], size_t row_stride = 32 * VEC)
+    {
+        float v[VEC][W];
+        float *row[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+        {
+            row[k] = msg + ((size_t)(code.base[k] + p) * row_stride + VEC * lane);
+            float t[VEC];
+            VecIO<VEC>::load(row[k], t);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                v[j][k] = t[j];
+        }
+        uint32_t syn_words[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            syn_words[j] = first ? 0u : synT[(size_t)p * VEC + j];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+            uint32_t xr = 0;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                xr ^= __float_as_uint(v[j][k]);
+            uint32_t sb;
+            if (first)
+            {
+                sb = xr & 1u; // Alice's bits ride in bit 0 during the first pass: their parity IS her syndrome bit
+                const uint32_t word = __ballot_sync(0xffffffffu, sb != 0);
+                if (lane == 0)
+                    synT[(size_t)p * VEC + j] = word;
+            }
+            else
+            {
+                sb = (syn_words[j] >> lane) & 1u;
+                bad[j] |= (xr ^ sb) & 1u;
+            }
+            xr ^= sb << 31;
+            Rule::template apply<W>(v[j], xr, cap);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+        {
+            float t[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                t[j] = v[j][k];
+            VecIO<VEC>::store(row[k], t);
+        }
+    }
+
+    // 32 x 32 bit transposes between frame-major packed words and the per-group node-major layout.
+    // in:  word `wd` of frames f0 + VEC*l + j (lane l)      out: T[(32*wd + b) * VEC + j] = word whose bit l is bit b of that frame's word
+    template <int VEC>
+    __device__ __forceinline__ void transpose_in(const uint32_t *__restrict__ frames, long long f0, long long n_frames, int words, int n, uint32_t *__restrict__ T)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int item = warp; item < words * VEC; item += nwarps)
+        {
+            const int wd = item / VEC, j = item % VEC;
+            const long long f = f0 + (long long)VEC * lane + j;
+            const uint32_t x = f < n_frames ? frames[f * words + wd] : 0u;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+            {
+                const uint32_t col = __ballot_sync(0xffffffffu, (x >> b) & 1u);
+                if (lane == b)
+                    mine = col;
+            }
+            const int bit = 32 * wd + lane;
+            if (bit < n)
+                T[(size_t)bit * VEC + j] = mine;
+        }
+    }
+    // fmap_g (optional): frame index of each of the group's 32 * VEC columns (0xFFFFFFFF = none) instead of f0 + column;
+    // keep[j] (with fmap_g): only the columns whose bit is set in keep[j] are written
+    template <int VEC>
+    __device__ __forceinline__ void transpose_out(const uint32_t *__restrict__ T, long long f0, long long n_frames, int words, int n, uint32_t *__restrict__ frames,
+                                                  const uint32_t *__restrict__ fmap_g = nullptr, const uint32_t *keep = nullptr)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int item = warp; item < words * VEC; item += nwarps)
+        {
+            const int wd = item / VEC, j = item % VEC;
+            const int bit = 32 * wd + lane;
+            const uint32_t x = bit < n ? T[(size_t)bit * VEC + j] : 0u;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l)
+            {
+                const uint32_t row = __ballot_sync(0xffffffffu, (x >> l) & 1u);
+                if (lane == l)
+                    mine = row;
+            }
+            long long f = f0 + (long long)VEC * lane + j;
+            if (fmap_g)
+            {
+                const uint32_t fm = fmap_g[VEC * lane + j];
+                f = (fm == 0xFFFFFFFFu || (keep && !((keep[j] >> lane) & 1u))) ? n_frames : (long long)fm;
+            }
+            if (f < n_frames)
+                frames[f * words + wd] = mine;
+        }
+    }
+
+}

@@ -1,4 +1,4 @@
-// Phase-split form of the frame-interleaved streaming decoder (qlb_stream_f32.cuh): same data layout (msg[slot][G], keys and
+// The frame-interleaved streaming decoder (layout and node helpers in qlb_stream_common.cuh): data layout (msg[slot][G], keys and
 // decisions bit-transposed per group), same node arithmetic (stream_check, the resident kernel's rules), but every pass of
 // the flooding schedule is its own kernel over ALL groups of the launch:
 //
@@ -18,7 +18,7 @@
 // kernel -- row-buffer locality, not occupancy, is what the gather lacks). Bookkeeping stays per group.
 // Results are bit-identical to the persistent kernel and to the SM-resident kernel (tests/test_gpu_codes.py).
 #pragma once
-#include "qlb_stream_f32.cuh"
+#include "qlb_stream_common.cuh"
 
 namespace qlb
 {

@@ -50,13 +50,13 @@ namespace qlb
                 for (int k = 0; k < max_cw; ++k)
                     if ((uint32_t)p < code.cnt[k])
                     {
-                        const double t = MathF64::tanh_half(msg[code.base[k] + p]);
+                        const double t = TwoPass<MathF64>::t(msg[code.base[k] + p]); // NaN stays NaN
                         msg[code.base[k] + p] = t;
                         row *= t;
                     }
                 for (int k = 0; k < max_cw; ++k)
                     if ((uint32_t)p < code.cnt[k])
-                        msg[code.base[k] + p] = clamp_msg(MathF64::two_atanh(row / msg[code.base[k] + p]), thr, en != 0);
+                        msg[code.base[k] + p] = TwoPass<MathF64>::out(MathF64::quotient(row, msg[code.base[k] + p]), en != 0, thr);
             }
             __syncthreads();
             if (keep)

@@ -11,12 +11,9 @@ namespace
     {
         auto kern = decode_resident_f32_kernel<Rule, kReconcile, kBW, kResidentThreads>;
         int kThreads = balanced_block_size(args.code, kResidentThreads, 0.55);
-        if (const char *e = std::getenv("QLB_RES32_THREADS")) // experiments only
-        {
-            const int t = std::atoi(e) / 32 * 32;
+        if (const int t = args.block_threads / 32 * 32) // qlb_decode_params.block_threads
             if (t >= 32 && t <= kResidentThreads && 32 * t >= args.code.n && 32 * t >= args.code.m)
                 kThreads = t;
-        }
         const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.slots, kBW);
         QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long grid = ctx->sm_count; // one resident CTA per SM

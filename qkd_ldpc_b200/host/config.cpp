@@ -85,6 +85,8 @@ config_data get_config_data(fs::path config_path)
             cfg.DEVICE_GPUS = static_cast<int>(root.at("device_gpus").as_size());
         if (root.contains("device_generate_keys"))
             cfg.DEVICE_GENERATE_KEYS = root.at("device_generate_keys").as_bool();
+        if (root.contains("device_force_allreduce"))
+            cfg.DEVICE_FORCE_ALLREDUCE = root.at("device_force_allreduce").as_bool();
         if (root.contains("device_batch_frames"))
         {
             cfg.DEVICE_BATCH_FRAMES = root.at("device_batch_frames").as_size();

@@ -137,6 +137,7 @@ int main(int argc, char **argv)
             throw std::runtime_error("Matrix folder is empty: " + matrix_dir.string());
         sim_inputs.resize(matrix_paths.size());
         prepare_sim_inputs(matrix_paths, sim_inputs);
+        qkd_b200::set_progress_directory(root / "results");
         const std::vector<sim_result> results = QKD_LDPC_batch_simulation(sim_inputs);
         for (sim_input &in : sim_inputs)
             free_matrix_H(in.matrix);

@@ -78,6 +78,7 @@ struct config_data
     int DEVICE_GPUS = 0;           // "device_gpus": 0 = all visible GPUs
     size_t DEVICE_BATCH_FRAMES = 32768; // "device_batch_frames": most frames per launch handed to one GPU (the on-device key generator needs
                                         // >= 32 k trials in flight to reach its 2.2 M frames/s: 4 096 -> 0.67 M, 16 384 -> 1.83 M; scripts/gen_timing2.py)
+    bool DEVICE_FORCE_ALLREDUCE = false; // "device_force_allreduce": run the statistics all-reduce through NCCL even on one GPU (tests)
     bool DEVICE_GENERATE_KEYS = true;  // "device_generate_keys": draw Alice/Bob on the GPU from the trial seeds (bit-exact with
                                        // generate_random_bit_array / introduce_errors); false = host threads generate
 };
@@ -170,6 +171,10 @@ namespace qkd_b200
         std::vector<point_report> points{};
     };
     const sweep_report &last_sweep_report();
+    // Where QKD_LDPC_batch_simulation appends every finished point while it runs (`ldpc(...).partial.csv` in the reference's
+    // format and `throughput(...).partial.csv`), so a 1 M-frame sweep holds nothing per trial and loses nothing on abort; the
+    // files are removed when the sweep completes and the caller writes the final ones. Empty (default): no progress files.
+    void set_progress_directory(const fs::path &directory);
     // Side file next to the reference-format CSV: per-point throughput, sifted-key rate, reconciliation efficiency
     // f = (1 - R) / h2(q) and leaked bits per frame (= M: plain syndrome coding). SURVEY.md 8f-3.
     void write_report(const sweep_report &report, fs::path directory);

@@ -17,6 +17,9 @@
 #include <functional>
 #include <iostream>
 #include <limits>
+#include <memory>
+#include <sstream>
+#include <algorithm>
 #include <mutex>
 #include <random>
 #include <stdexcept>
@@ -85,15 +88,12 @@ namespace
     // One batch of frames travelling host -> GPU -> host.
     struct batch
     {
-        size_t first_trial = 0, frames = 0;
-        bool on_device = false;           // keys are generated on the GPU from seeds[first_trial ...] + seed_offset
-        uint64_t seed_offset = 0;
-        double requested_qber = 0;
-        std::vector<uint32_t> alice, bob; // packed keys
-        std::vector<double> qber;         // exact QBER per frame
-        std::vector<uint32_t> iterations;
-        std::vector<uint8_t> result;
+        size_t point = 0, first_trial = 0, frames = 0; // trial seeds[first_trial ...] + point (src/simulation.cpp:247)
+        bool on_device = false;           // keys are generated on the GPU from the trial seeds
+        std::vector<uint32_t> alice, bob; // packed keys (host generation)
+        std::vector<double> qber;         // exact QBER per frame (host generation)
         std::atomic<size_t> parts_left{0};
+
     };
 
     // Thread-safe queue of batch pointers (nullptr = shut down).
@@ -247,6 +247,8 @@ void prepare_sim_inputs(const std::vector<fs::path> &matrix_paths, std::vector<s
         in.matrix_path = matrix_paths[i];
         for (const std::string &warning : qkd_b200::matrix_warnings(in.matrix))
             std::cerr << "WARNING (" << matrix_paths[i].filename().string() << "): " << warning << "\n";
+        if (!CFG.INTERACTIVE_MODE)
+            qkd_b200::code_for(in.matrix); // a matrix the device layout rejects must stop the run here, before any GPU work
         const double code_rate = 1. - (static_cast<double>(in.matrix.num_check_nodes) / in.matrix.num_bit_nodes);
         in.QBER = get_rate_based_QBER_range(code_rate, CFG.R_QBER_PARAMETERS);
     }
@@ -332,333 +334,472 @@ trial_result run_trial(const H_matrix &matrix, const double QBER, size_t seed)
     return result;
 }
 
+namespace
+{
+    // Integer statistics of one (matrix, QBER) point: histogram of iterations_num over the frames whose syndromes match, then
+    // {n_sp, n_ldpc, n_trials, sum of iterations}. Everything the reference accumulates per point (src/simulation.cpp:252-312) is a
+    // function of these integers, so the sums over workers / GPUs do not depend on who decoded what, nor on the reduction order.
+    struct point_stats_view
+    {
+        const uint64_t *v;
+        size_t max_it;
+        uint64_t n_sp() const { return v[max_it + 1]; }
+        uint64_t n_ldpc() const { return v[max_it + 2]; }
+        uint64_t n_trials() const { return v[max_it + 3]; }
+        uint64_t iterations() const { return v[max_it + 4]; }
+    };
+
+    // src/simulation.cpp:252-312 from the histogram: count / min / max / mean / population std-dev over the successful frames.
+    // The mean is a sum of integers (exact in double, as the reference's running sum is); the std-dev sums (it - mean)^2 per
+    // iteration count instead of per trial -- the same real number, rounded differently far below the CSV's six digits.
+    void fill_result(sim_result &r, const point_stats_view &st, size_t trials)
+    {
+        const size_t max_it = st.max_it;
+        size_t it_max = 0, it_min = max_it;
+        double mean = 0, sd = 0;
+        if (st.n_sp() > 0)
+        {
+            uint64_t sum = 0;
+            for (size_t it = 0; it <= max_it; ++it)
+                if (st.v[it])
+                {
+                    sum += st.v[it] * it;
+                    it_max = std::max(it_max, it);
+                    it_min = std::min(it_min, it);
+                }
+            mean = static_cast<double>(sum) / static_cast<double>(st.n_sp());
+            for (size_t it = 0; it <= max_it; ++it)
+                if (st.v[it])
+                    sd += static_cast<double>(st.v[it]) * pow(static_cast<double>(it) - mean, 2);
+            sd = sqrt(sd / static_cast<double>(st.n_sp()));
+        }
+        r.iterations_successful_sp_max = it_max;
+        r.iterations_successful_sp_min = (it_min == max_it) ? 0 : it_min; // :306
+        r.iterations_successful_sp_mean = mean;
+        r.iterations_successful_sp_std_dev = sd;
+        r.ratio_trials_successful_ldpc = static_cast<double>(st.n_ldpc()) / trials;
+        r.ratio_trials_successful_sp = static_cast<double>(st.n_sp()) / trials;
+    }
+
+    fs::path g_progress_dir; // where finished points are appended while the sweep runs (empty: nowhere)
+
+    std::string csv_row(const sim_result &r)
+    {
+        std::ostringstream out;
+        out << r.sim_number << ";" << r.matrix_filename << ";" << (r.is_regular ? "regular" : "irregular") << ";"
+            << 1. - (static_cast<double>(r.num_check_nodes) / r.num_bit_nodes) << ";" << r.num_check_nodes << ";" << r.num_bit_nodes << ";"
+            << r.initial_QBER << ";" << r.iterations_successful_sp_mean << ";" << r.iterations_successful_sp_std_dev << ";"
+            << r.iterations_successful_sp_min << ";" << r.iterations_successful_sp_max << ";" << r.ratio_trials_successful_sp << ";"
+            << r.ratio_trials_successful_ldpc << ";" << 1. - r.ratio_trials_successful_ldpc << "\n";
+        return out.str();
+    }
+    const char *kCsvHeader = "№;MATRIX_FILENAME;TYPE;CODE_RATE;M;N;QBER;ITERATIONS_SUCCESSFUL_SP_MEAN;ITERATIONS_SUCCESSFUL_SP_STD_DEV;"
+                             "ITERATIONS_SUCCESSFUL_SP_MIN;ITERATIONS_SUCCESSFUL_SP_MAX;RATIO_TRIALS_SUCCESSFUL_SP;RATIO_TRIALS_SUCCESSFUL_LDPC;FER\n";
+    const char *kReportHeader = "SIM;MATRIX_FILENAME;M;N;QBER;FRAMES;SECONDS;FRAMES_PER_S;SIFTED_MBIT_PER_S;FRAME_ITERATIONS;MEAN_ITERATIONS;"
+                                "EFFICIENCY_F;LEAKED_BITS_PER_FRAME;GPUS;PRECISION\n";
+    std::string report_row(const qkd_b200::point_report &p, int gpus)
+    {
+        std::ostringstream out;
+        const std::string precision = CFG.DEVICE_PRECISION == 32 ? (CFG.DEVICE_FP32_FAST ? "fp32-fast" : "fp32") : (CFG.DEVICE_FP64_FUSED ? "fp64-fused" : "fp64");
+        const double q = p.exact_qber, h2 = -q * std::log2(q) - (1. - q) * std::log2(1. - q);
+        const double fps = p.seconds > 0 ? p.frames / p.seconds : 0.;
+        out << p.sim_number << ";" << p.matrix_filename << ";" << p.num_check_nodes << ";" << p.num_bit_nodes << ";" << q << ";" << p.frames << ";"
+            << p.seconds << ";" << fps << ";" << fps * p.num_bit_nodes / 1e6 << ";" << p.frame_iterations << ";"
+            << static_cast<double>(p.frame_iterations) / p.frames << ";" << (static_cast<double>(p.num_check_nodes) / p.num_bit_nodes) / h2 << ";"
+            << p.num_check_nodes << ";" << gpus << ";" << precision << "\n";
+        return out.str();
+    }
+}
+
+namespace qkd_b200
+{
+    void set_progress_directory(const fs::path &directory) { g_progress_dir = directory; }
+}
+
+// The frame-batch scheduler. Every (point, block of trials) is an independent batch; ALL batches of the sweep are queued at
+// once -- there is no barrier between QBER points -- and dealt to two host threads per GPU, each with a context (stream +
+// staging buffers) of its own. Workers accumulate integer statistics per point; a finished point is appended to the progress
+// files at once (nothing is held per trial, nothing is lost on abort). The statistics of the returned results come from the
+// sweep's ONE collective: a SUM all-reduce over the GPUs of the [points x (max_it + 5)] integers (qlb_stats_allreduce, NCCL).
 std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &sim_in)
 {
     using clock = std::chrono::steady_clock;
     const auto t_start = clock::now();
-    const bool timing = std::getenv("QKD_B200_TIMING") != nullptr; // coarse wall-clock marks on stderr
-    auto mark = [&](const char *what)
-    {
-        if (timing)
-            std::fprintf(stderr, "[timing] %8.3f s  %s\n", std::chrono::duration<double>(clock::now() - t_start).count(), what);
-    };
+    auto seconds_since = [](clock::time_point t0) { return std::chrono::duration<double>(clock::now() - t0).count(); };
     const size_t trials = CFG.TRIALS_NUMBER;
-    size_t points_total = 0;
-    for (const sim_input &in : sim_in)
-        points_total += in.QBER.size();
+    const size_t max_it = CFG.SUM_PRODUCT_MAX_ITERATIONS;
+    const size_t stats_width = max_it + 1 + 4;
 
-    // seeds[k]: the k-th raw output of xoshiro256++(SIMULATION_SEED), drawn the way the reference draws them
+    // seeds[k]: the k-th raw output of xoshiro256++(SIMULATION_SEED), drawn the way the reference draws them (:222-228)
     XoshiroCpp::Xoshiro256PlusPlus seed_prng(CFG.SIMULATION_SEED);
     std::uniform_int_distribution<size_t> any_size(0, std::numeric_limits<size_t>::max());
     std::vector<size_t> seeds(trials);
     for (size_t &s : seeds)
         s = any_size(seed_prng);
 
-    mark("trial seeds drawn");
+    // ---- the points of the sweep, numbered as the reference numbers them (curr_sim, :231-236, 312) ------------------------
+    struct point
+    {
+        const sim_input *in;
+        double qber, exact_qber;
+        qlb_code *code;
+        std::atomic<size_t> batches_left{0};
+        std::atomic<uint64_t> device_ns{0};
+    };
+    size_t points_total = 0;
+    for (const sim_input &in : sim_in)
+        points_total += in.QBER.size();
+    std::vector<point> points(points_total);
+    {
+        size_t pt = 0;
+        for (const sim_input &in : sim_in)
+            for (const double q : in.QBER)
+            {
+                const size_t n = in.matrix.num_bit_nodes;
+                if (static_cast<size_t>(n * q) == 0)
+                    key_too_small(n); // the reference throws from inside the point's first trial (src/simulation.cpp:170-175)
+                points[pt].in = &in;
+                points[pt].qber = q;
+                points[pt].exact_qber = static_cast<double>(static_cast<size_t>(n * q)) / n; // introduce_errors' return value (:436-459)
+                points[pt].code = qkd_b200::code_for(in.matrix);
+                ++pt;
+            }
+    }
+
     int gpus = qkd_b200::usable_devices();
     if (gpus < 1)
         throw std::runtime_error("no CUDA device is available: this build has no CPU decoder");
     if (CFG.DEVICE_GPUS > 0)
         gpus = std::min(gpus, CFG.DEVICE_GPUS);
-    // device_batch_frames is the upper bound; with many GPUs the batches shrink so that every worker still gets ~8 of them per
-    // QBER point (the point ends with a barrier: 61 batches over 16 workers would leave a quarter of them idle at the end)
-    const size_t batch_cap = std::max<size_t>(1, CFG.DEVICE_BATCH_FRAMES);
-    const size_t batch_frames = std::min(batch_cap, std::max<size_t>(1024, trials / (static_cast<size_t>(gpus) * 2 * 8) + 1));
-    const size_t max_it = CFG.SUM_PRODUCT_MAX_ITERATIONS;
     const qlb_decode_params params = qkd_b200::params_from_cfg(max_it, CFG.SUM_PRODUCT_MSG_LLR_THRESHOLD);
-    const size_t stats_width = max_it + 1 + 4; // histogram of iterations of successful frames + {n_sp, n_ldpc, n_trials, sum_iterations}
-
-    worker_pool generators(CFG.THREADS_NUMBER);
-    const size_t gen_parts = std::max<size_t>(1, CFG.THREADS_NUMBER);
-    // two host threads (and contexts/streams) per GPU: one batch's key generation and transfers overlap another's decode
-    const int workers_per_gpu = 2, workers = gpus * workers_per_gpu;
-    std::vector<batch> pool(static_cast<size_t>(workers) * 2 + 1);
-    batch_queue free_batches, ready;
-    for (batch &b : pool)
-        free_batches.push(&b);
-
-    // ---- GPU workers: one host thread + one context per GPU ---------------------------------------------------------
-    std::vector<trial_result> trial_results(trials);
-    std::vector<std::vector<uint64_t>> gpu_stats(workers, std::vector<uint64_t>(stats_width, 0)); // per worker, folded per GPU below
-    std::vector<qlb_ctx *> contexts(workers, nullptr);
-    std::atomic<size_t> batches_done{0};
-    std::mutex err_mu, done_mu;
-    std::condition_variable done_cv;
-    std::string first_error;
-    qlb_code *code = nullptr;                 // the current matrix
-    std::atomic<uint64_t> device_ns{0}, ready_ns{0};
-    std::atomic<int> contexts_ready{0};
-    std::vector<std::thread> gpu_threads;
-    // integer statistics of one finished trial: histogram of iterations of successful frames + {n_sp, n_ldpc, n_trials, sum_iterations}
-    auto account = [max_it](std::vector<uint64_t> &st, const trial_result &tr)
+    g_report = qkd_b200::sweep_report{};
+    std::vector<sim_result> sim_results(points_total);
+    for (size_t pt = 0; pt < points_total; ++pt)
     {
-        const size_t it = tr.ldpc_res.sp_res.iterations_num;
-        if (tr.ldpc_res.sp_res.syndromes_match)
-        {
-            ++st[std::min<size_t>(it, max_it)];
-            ++st[max_it + 1];
-            st[max_it + 2] += tr.ldpc_res.keys_match;
-        }
-        ++st[max_it + 3];
-        st[max_it + 4] += it;
+        const H_matrix &h = points[pt].in->matrix;
+        sim_result &r = sim_results[pt];
+        r.sim_number = pt;
+        r.matrix_filename = points[pt].in->matrix_path.filename().string();
+        r.is_regular = h.is_regular;
+        r.num_bit_nodes = h.num_bit_nodes;
+        r.num_check_nodes = h.num_check_nodes;
+        r.initial_QBER = points[pt].exact_qber; // the reference copies trial 0's (:304); every trial of a point has the same
+    }
+    auto report_of = [&](size_t pt, uint64_t frame_iterations, double seconds)
+    {
+        qkd_b200::point_report pr;
+        pr.sim_number = pt;
+        pr.matrix_filename = sim_results[pt].matrix_filename;
+        pr.num_bit_nodes = sim_results[pt].num_bit_nodes;
+        pr.num_check_nodes = sim_results[pt].num_check_nodes;
+        pr.exact_qber = points[pt].exact_qber;
+        pr.frames = trials;
+        pr.frame_iterations = frame_iterations;
+        pr.seconds = seconds;
+        return pr;
     };
-    // With any console trace enabled the trials of a point run one after another on this thread through run_trial, so the
-    // output reads like the reference's with threads_number = 1 (its pool would interleave the prints of concurrent trials).
+
+    // progress files: one row per finished point, flushed as it finishes; removed when the sweep completes
+    std::ofstream progress_csv, progress_report;
+    fs::path progress_csv_path, progress_report_path;
+    if (!g_progress_dir.empty())
+    {
+        fs::create_directories(g_progress_dir);
+        const std::string tag = "(trial_num=" + std::to_string(trials) + ",max_sum_prod_iters=" + std::to_string(max_it) + ",seed=" +
+                                std::to_string(CFG.SIMULATION_SEED) + ").partial.csv";
+        progress_csv_path = g_progress_dir / ("ldpc" + tag);
+        progress_report_path = g_progress_dir / ("throughput" + tag);
+        progress_csv.open(progress_csv_path, std::ios::out | std::ios::trunc);
+        progress_report.open(progress_report_path, std::ios::out | std::ios::trunc);
+        progress_csv << kCsvHeader << std::flush;
+        progress_report << kReportHeader << std::flush;
+    }
+    auto flush_point = [&](size_t pt, const uint64_t *stats, double seconds)
+    {
+        sim_result r = sim_results[pt];
+        fill_result(r, point_stats_view{stats, max_it}, trials);
+        if (progress_csv.is_open())
+        {
+            progress_csv << csv_row(r) << std::flush;
+            progress_report << report_row(report_of(pt, stats[max_it + 4], seconds), gpus) << std::flush;
+        }
+    };
+
+    // With any console trace enabled the trials run one after another on this thread through run_trial, so the output reads
+    // like the reference's with threads_number = 1 (its pool would interleave the prints of concurrent trials).
     const bool traced = CFG.TRACE_QKD_LDPC || CFG.TRACE_SUM_PRODUCT || CFG.TRACE_SUM_PRODUCT_LLR;
-    for (int g = 0; g < workers; ++g)
-        gpu_threads.emplace_back([&, g]
-                                 {
-            try { contexts[g] = qkd_b200::context(g % gpus); } // worker g drives GPU g % gpus with its own context
-            catch (const std::exception &e) { std::lock_guard<std::mutex> lk(err_mu); if (first_error.empty()) first_error = e.what(); }
-            if (++contexts_ready == workers)
+    // per GPU: [points x stats_width]; the all-reduce at the end sums them
+    std::vector<std::vector<uint64_t>> gpu_stats(gpus, std::vector<uint64_t>(points_total * stats_width, 0));
+    std::vector<double> point_seconds(points_total, 0.);
+    double startup_seconds = 0., device_seconds = 0.;
+
+    if (traced)
+    {
+        for (size_t pt = 0; pt < points_total; ++pt)
+        {
+            const auto t0 = clock::now();
+            uint64_t *st = gpu_stats[0].data() + pt * stats_width;
+            for (size_t k = 0; k < trials; ++k)
             {
-                ready_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(clock::now() - t_start).count();
-                mark("every worker has its context");
-            }
-            for (;;)
-            {
-                batch *b = ready.pop();
-                if (!b)
-                    return;
-                if (contexts[g] && first_error.empty())
+                const trial_result tr = run_trial(points[pt].in->matrix, points[pt].qber, seeds[k] + pt);
+                const size_t it = tr.ldpc_res.sp_res.iterations_num;
+                if (tr.ldpc_res.sp_res.syndromes_match)
                 {
-                    const auto t0 = clock::now();
-                    int rc;
-                    if (b->on_device)
+                    ++st[std::min<size_t>(it, max_it)];
+                    ++st[max_it + 1];
+                    st[max_it + 2] += tr.ldpc_res.keys_match;
+                }
+                ++st[max_it + 3];
+                st[max_it + 4] += it;
+            }
+            point_seconds[pt] = seconds_since(t0);
+            flush_point(pt, st, point_seconds[pt]);
+        }
+    }
+    else
+    {
+        // ---- batches ----------------------------------------------------------------------------------------------------
+        const int workers_per_gpu = 2, workers = gpus * workers_per_gpu;
+        const size_t batch_cap = std::max<size_t>(1, CFG.DEVICE_BATCH_FRAMES);
+        // enough batches for every worker to get several, but none smaller than 1 024 frames (a launch fills 148 SMs)
+        const size_t batch_frames = std::max<size_t>(1, std::min(batch_cap, std::max<size_t>(1024, trials * points_total / (static_cast<size_t>(workers) * 4) + 1)));
+        const size_t batches_per_point = (trials + batch_frames - 1) / batch_frames;
+        for (point &p : points)
+            p.batches_left = batches_per_point;
+        // costly points first (high QBER = many iterations): the sweep then ends on short batches, which keeps the tail of the
+        // last GPU short; nothing else depends on the order
+        std::vector<size_t> order(points_total);
+        for (size_t pt = 0; pt < points_total; ++pt)
+            order[pt] = pt;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return points[a].qber > points[b].qber; });
+
+        batch_queue free_batches, ready;
+        std::vector<batch> pool(CFG.DEVICE_GENERATE_KEYS ? 0 : static_cast<size_t>(workers) * 2 + 1);
+        for (batch &b : pool)
+            free_batches.push(&b);
+        std::vector<batch> descriptors; // device-generated batches carry no host buffers: one descriptor each, queued up front
+        if (CFG.DEVICE_GENERATE_KEYS)
+            descriptors = std::vector<batch>(points_total * batches_per_point);
+
+        std::atomic<bool> failed{false};
+        std::mutex err_mu, done_mu;
+        std::condition_variable done_cv;
+        std::string first_error;
+        auto record_error = [&](const std::string &what)
+        {
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (first_error.empty())
+                first_error = what;
+            failed = true;
+        };
+        std::vector<size_t> finished; // points whose last batch is done, in completion order (guarded by done_mu)
+        std::atomic<int> contexts_ready{0};
+        std::atomic<uint64_t> device_ns{0};
+        // per worker: [points x stats_width] (no sharing while decoding), folded per GPU as points finish
+        std::vector<std::vector<uint64_t>> worker_stats(workers, std::vector<uint64_t>(points_total * stats_width, 0));
+        std::vector<std::thread> gpu_threads;
+        for (int g = 0; g < workers; ++g)
+            gpu_threads.emplace_back([&, g]
+                                     {
+                qlb_ctx *ctx = nullptr;
+                try { ctx = qkd_b200::context(g % gpus); } // worker g drives GPU g % gpus with its own context
+                catch (const std::exception &e) { record_error(e.what()); }
+                if (++contexts_ready == workers)
+                    startup_seconds = seconds_since(t_start);
+                std::vector<uint32_t> iterations;
+                std::vector<uint8_t> result;
+                for (;;)
+                {
+                    batch *b = ready.pop();
+                    if (!b)
+                        return;
+                    point &p = points[b->point];
+                    if (ctx && !failed)
                     {
-                        double exact = 0;
-                        rc = qlb_run_trials(contexts[g], code, &params, static_cast<int64_t>(b->frames), reinterpret_cast<const uint64_t *>(&seeds[b->first_trial]),
-                                            b->seed_offset, b->requested_qber, b->iterations.data(), b->result.data(), &exact);
-                        std::fill(b->qber.begin(), b->qber.end(), exact);
-                    }
-                    else
-                        rc = qlb_reconcile_batch_packed(contexts[g], code, &params, static_cast<int64_t>(b->frames), b->alice.data(), b->bob.data(),
-                                                        b->qber.data(), b->iterations.data(), b->result.data(), nullptr, nullptr);
-                    device_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(clock::now() - t0).count();
-                    if (rc != QLB_OK)
-                    {
-                        std::lock_guard<std::mutex> lk(err_mu);
-                        if (first_error.empty())
-                            first_error = qlb_last_error();
-                    }
-                    else
-                    {
-                        for (size_t f = 0; f < b->frames; ++f)
+                        iterations.resize(b->frames);
+                        result.resize(b->frames);
+                        const auto t0 = clock::now();
+                        int rc;
+                        if (b->on_device)
                         {
-                            trial_result &tr = trial_results[b->first_trial + f];
-                            tr.ldpc_res.sp_res.iterations_num = b->iterations[f];
-                            tr.ldpc_res.sp_res.syndromes_match = (b->result[f] & QLB_RES_SYNDROMES_MATCH) != 0;
-                            tr.ldpc_res.keys_match = (b->result[f] & QLB_RES_KEYS_MATCH) != 0;
-                            tr.initial_QBER = b->qber[f];
-                            account(gpu_stats[g], tr);
+                            double exact = 0;
+                            rc = qlb_run_trials(ctx, p.code, &params, static_cast<int64_t>(b->frames), reinterpret_cast<const uint64_t *>(&seeds[b->first_trial]),
+                                                b->point, p.qber, iterations.data(), result.data(), &exact);
+                        }
+                        else
+                            rc = qlb_reconcile_batch_packed(ctx, p.code, &params, static_cast<int64_t>(b->frames), b->alice.data(), b->bob.data(),
+                                                            b->qber.data(), iterations.data(), result.data(), nullptr, nullptr);
+                        const uint64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(clock::now() - t0).count();
+                        device_ns += ns;
+                        p.device_ns += ns;
+                        if (rc != QLB_OK)
+                            record_error(qlb_last_error());
+                        else
+                        {
+                            uint64_t *st = worker_stats[g].data() + b->point * stats_width;
+                            for (size_t f = 0; f < b->frames; ++f)
+                            {
+                                const size_t it = iterations[f];
+                                if (result[f] & QLB_RES_SYNDROMES_MATCH)
+                                {
+                                    ++st[std::min<size_t>(it, max_it)];
+                                    ++st[max_it + 1];
+                                    st[max_it + 2] += (result[f] & QLB_RES_KEYS_MATCH) != 0;
+                                }
+                                ++st[max_it + 3];
+                                st[max_it + 4] += it;
+                            }
                         }
                     }
-                }
-                free_batches.push(b);
-                {
-                    std::lock_guard<std::mutex> lk(done_mu);
-                    ++batches_done;
-                }
-                done_cv.notify_all();
-            } });
-    // The sweep's ONE collective is a single NCCL all-reduce of the integer statistics of every point, at the end. Creating
-    // the communicators takes seconds on an 8-GPU box, so it happens on a side thread (with contexts of its own) while the
-    // GPUs decode.
-    const bool reduce_over_nccl = gpus > 1 || std::getenv("QKD_B200_FORCE_ALLREDUCE");
-    std::vector<std::vector<uint64_t>> sweep_stats(gpus, std::vector<uint64_t>(points_total * stats_width, 0));
-    std::string warm_error;
-    std::thread nccl_warm_up;
-    if (reduce_over_nccl)
-        nccl_warm_up = std::thread([&]
-                                   {
-            try
-            {
-                std::vector<qlb_ctx *> ctxs;
-                std::vector<uint64_t> zero(gpus, 0);
-                std::vector<uint64_t *> ptrs;
-                for (int g = 0; g < gpus; ++g)
-                {
-                    ctxs.push_back(qkd_b200::context(g));
-                    ptrs.push_back(&zero[g]);
-                }
-                qkd_b200::check(qlb_stats_allreduce(ctxs.data(), gpus, ptrs.data(), 1), "qlb_stats_allreduce (communicator set-up)");
-                mark("NCCL communicators ready");
-            }
-            catch (const std::exception &e) { warm_error = e.what(); } });
-    auto shut_down = [&]
-    {
-        for (int g = 0; g < workers; ++g)
-            ready.push(nullptr);
-        for (auto &t : gpu_threads)
-            t.join();
-        if (nccl_warm_up.joinable())
-            nccl_warm_up.join();
-    };
-
-    std::vector<sim_result> sim_results(points_total);
-    size_t curr_sim = 0, frames_total = 0, iterations_total = 0;
-    std::vector<size_t> point_ok_sp, point_ok_ldpc;
-    g_report = qkd_b200::sweep_report{};
-    try
-    {
-        for (const sim_input &in : sim_in)
+                    const size_t pt = b->point;
+                    if (!b->on_device)
+                        free_batches.push(b);
+                    if (p.batches_left.fetch_sub(1, std::memory_order_acq_rel) == 1) // every worker's share of this point is in
+                    {
+                        std::lock_guard<std::mutex> lk(done_mu);
+                        finished.push_back(pt);
+                        done_cv.notify_all();
+                    }
+                } });
+        auto shut_down = [&]
         {
-            const H_matrix &matrix = in.matrix;
-            const size_t n = matrix.num_bit_nodes, words = (n + 31) / 32;
-            code = qkd_b200::code_for(matrix);
-            mark("code layout ready");
-            const std::string matrix_filename = in.matrix_path.filename().string();
-            for (const double QBER : in.QBER)
+            for (int g = 0; g < workers; ++g)
+                ready.push(nullptr);
+            for (auto &t : gpu_threads)
+                t.join();
+        };
+
+        try
+        {
+            // ---- issue every batch of the sweep; flush points as they finish -------------------------------------------------
+            std::unique_ptr<worker_pool> generators;
+            const size_t gen_parts = std::max<size_t>(1, CFG.THREADS_NUMBER);
+            if (!CFG.DEVICE_GENERATE_KEYS)
+                generators = std::make_unique<worker_pool>(CFG.THREADS_NUMBER);
+            size_t next_descriptor = 0, flushed = 0;
+            auto flush_finished = [&](bool wait_for_all)
             {
-                if (static_cast<size_t>(n * QBER) == 0)
-                    key_too_small(n); // the reference throws from inside the first trial (src/simulation.cpp:170-175)
-                const auto t_point = clock::now();
-                for (auto &st : gpu_stats)
-                    std::fill(st.begin(), st.end(), 0);
-                batches_done = 0;
-                size_t issued = 0;
-                for (size_t k = 0; traced && k < trials; ++k)
+                std::unique_lock<std::mutex> lk(done_mu);
+                for (;;)
                 {
-                    trial_results[k] = run_trial(matrix, QBER, seeds[k] + curr_sim);
-                    account(gpu_stats[0], trial_results[k]);
+                    while (flushed < finished.size())
+                    {
+                        const size_t pt = finished[flushed++];
+                        lk.unlock();
+                        for (int w = 0; w < workers; ++w)
+                        {
+                            const uint64_t *src = worker_stats[w].data() + pt * stats_width;
+                            uint64_t *acc = gpu_stats[w % gpus].data() + pt * stats_width;
+                            for (size_t x = 0; x < stats_width; ++x)
+                                acc[x] += src[x];
+                        }
+                        std::vector<uint64_t> sum(stats_width, 0);
+                        for (int g = 0; g < gpus; ++g)
+                            for (size_t x = 0; x < stats_width; ++x)
+                                sum[x] += gpu_stats[g][pt * stats_width + x];
+                        point_seconds[pt] = points[pt].device_ns.load() * 1e-9 / workers;
+                        flush_point(pt, sum.data(), point_seconds[pt]);
+                        lk.lock();
+                    }
+                    if (!wait_for_all || flushed == points_total || failed)
+                        return;
+                    done_cv.wait(lk, [&] { return flushed < finished.size() || failed.load(); });
                 }
-                for (size_t first = 0; !traced && first < trials; first += batch_frames, ++issued)
+            };
+            for (const size_t pt : order)
+            {
+                const point &p = points[pt];
+                const size_t n = p.in->matrix.num_bit_nodes, words = (n + 31) / 32;
+                for (size_t first = 0; first < trials && !failed; first += batch_frames)
                 {
-                    batch *b = free_batches.pop();
+                    batch *b = CFG.DEVICE_GENERATE_KEYS ? &descriptors[next_descriptor++] : free_batches.pop();
+                    b->point = pt;
                     b->first_trial = first;
                     b->frames = std::min(batch_frames, trials - first);
-                    b->qber.resize(b->frames);
-                    b->iterations.resize(b->frames);
-                    b->result.resize(b->frames);
                     b->on_device = CFG.DEVICE_GENERATE_KEYS;
-                    b->seed_offset = curr_sim;
-                    b->requested_qber = QBER;
                     if (b->on_device)
                     {
                         ready.push(b); // nothing to prepare on the host: the trial seeds are the input
                         continue;
                     }
+                    b->qber.resize(b->frames);
                     b->alice.resize(b->frames * words);
                     b->bob.resize(b->frames * words);
                     const size_t parts = std::min(gen_parts, b->frames);
                     b->parts_left = parts;
+                    const double QBER = p.qber;
                     for (size_t part = 0; part < parts; ++part)
-                        generators.submit([&, b, part, parts, n, words, QBER, curr_sim]
-                                          {
-                            std::vector<int> alice(n), bob(n);
-                            const size_t lo = b->frames * part / parts, hi = b->frames * (part + 1) / parts;
-                            for (size_t f = lo; f < hi; ++f)
-                                b->qber[f] = make_frame(n, QBER, seeds[b->first_trial + f] + curr_sim, alice, bob, &b->alice[f * words], &b->bob[f * words]);
-                            if (--b->parts_left == 0)
-                                ready.push(b); });
+                        generators->submit([&, b, part, parts, n, words, QBER, pt]
+                                           {
+                                try
+                                {
+                                    std::vector<int> alice(n), bob(n);
+                                    const size_t lo = b->frames * part / parts, hi = b->frames * (part + 1) / parts;
+                                    for (size_t f = lo; f < hi; ++f)
+                                        b->qber[f] = make_frame(n, QBER, seeds[b->first_trial + f] + pt, alice, bob, &b->alice[f * words], &b->bob[f * words]);
+                                }
+                                catch (const std::exception &e) { record_error(e.what()); } // the batch still travels: its point must finish
+                                if (--b->parts_left == 0)
+                                    ready.push(b); });
+                    flush_finished(false);
                 }
-                {
-                    std::unique_lock<std::mutex> lk(done_mu);
-                    done_cv.wait(lk, [&] { return batches_done == issued; });
-                }
-                if (!first_error.empty())
-                    throw std::runtime_error(first_error);
-                mark("point decoded");
-
-                // fold the second worker of each GPU into the first and keep the point's per-GPU integer statistics for the
-                // all-reduce at the end of the sweep
-                for (int w = gpus; w < workers; ++w)
-                    for (size_t x = 0; x < stats_width; ++x)
-                        gpu_stats[w % gpus][x] += gpu_stats[w][x];
-                for (int g = 0; g < gpus; ++g)
-                    std::copy(gpu_stats[g].begin(), gpu_stats[g].end(), sweep_stats[g].begin() + static_cast<std::ptrdiff_t>(curr_sim * stats_width));
-
-                // statistics exactly as the reference accumulates them, in trial order (src/simulation.cpp:252-312)
-                size_t ok_sp = 0, ok_ldpc = 0, it_max = 0, it_min = max_it;
-                double mean = 0, sd = 0;
-                for (const trial_result &tr : trial_results)
-                    if (tr.ldpc_res.sp_res.syndromes_match)
-                    {
-                        const size_t it = tr.ldpc_res.sp_res.iterations_num;
-                        ++ok_sp;
-                        it_max = std::max(it_max, it);
-                        it_min = std::min(it_min, it);
-                        ok_ldpc += tr.ldpc_res.keys_match;
-                        mean += static_cast<double>(it);
-                    }
-                if (ok_sp > 0)
-                {
-                    mean /= static_cast<double>(ok_sp);
-                    for (const trial_result &tr : trial_results)
-                        if (tr.ldpc_res.sp_res.syndromes_match)
-                            sd += pow(static_cast<double>(tr.ldpc_res.sp_res.iterations_num) - mean, 2);
-                    sd = sqrt(sd / static_cast<double>(ok_sp));
-                }
-                point_ok_sp.push_back(ok_sp);
-                point_ok_ldpc.push_back(ok_ldpc);
-
-                sim_result &r = sim_results[curr_sim];
-                r.sim_number = curr_sim;
-                r.matrix_filename = matrix_filename;
-                r.is_regular = matrix.is_regular;
-                r.num_bit_nodes = matrix.num_bit_nodes;
-                r.num_check_nodes = matrix.num_check_nodes;
-                r.initial_QBER = trial_results[0].initial_QBER;
-                r.iterations_successful_sp_max = it_max;
-                r.iterations_successful_sp_min = (it_min == max_it) ? 0 : it_min;
-                r.iterations_successful_sp_mean = mean;
-                r.iterations_successful_sp_std_dev = sd;
-                r.ratio_trials_successful_ldpc = static_cast<double>(ok_ldpc) / trials;
-                r.ratio_trials_successful_sp = static_cast<double>(ok_sp) / trials;
-                frames_total += trials;
-                qkd_b200::point_report pr;
-                pr.sim_number = curr_sim;
-                pr.matrix_filename = matrix_filename;
-                pr.num_bit_nodes = matrix.num_bit_nodes;
-                pr.num_check_nodes = matrix.num_check_nodes;
-                pr.exact_qber = r.initial_QBER;
-                pr.frames = trials;
-                pr.frame_iterations = 0; // filled from the reduced statistics below
-                pr.seconds = std::chrono::duration<double>(clock::now() - t_point).count();
-                g_report.points.push_back(pr);
-                mark("point statistics done");
-                ++curr_sim;
             }
+            flush_finished(true); // returns early on failure; the workers skip whatever is still queued
         }
-    }
-    catch (...)
-    {
+        catch (...)
+        {
+            shut_down();
+            throw;
+        }
         shut_down();
-        throw;
+        if (failed)
+            throw std::runtime_error(first_error);
+        device_seconds = device_ns.load() * 1e-9 / workers;
     }
-    shut_down();
 
     // ---- the sweep's one collective: SUM all-reduce of [points x (max_it + 5)] integers over the GPUs of this box -----------
-    if (reduce_over_nccl && !traced)
+    // Communicators are created here, on this thread, after every worker has stopped: NCCL set-up next to threads that launch
+    // kernels and (re)allocate device buffers is the documented multi-thread deadlock pattern.
+    const bool reduce_over_nccl = !traced && (gpus > 1 || CFG.DEVICE_FORCE_ALLREDUCE);
+    if (reduce_over_nccl)
     {
-        if (!warm_error.empty())
-            throw std::runtime_error(warm_error);
         std::vector<qlb_ctx *> ctxs;
         std::vector<uint64_t *> ptrs;
         for (int g = 0; g < gpus; ++g)
         {
             ctxs.push_back(qkd_b200::context(g));
-            ptrs.push_back(sweep_stats[g].data());
+            ptrs.push_back(gpu_stats[g].data());
         }
-        qkd_b200::check(qlb_stats_allreduce(ctxs.data(), gpus, ptrs.data(), sweep_stats[0].size()), "qlb_stats_allreduce");
-        mark("statistics all-reduced");
+        qkd_b200::check(qlb_stats_allreduce(ctxs.data(), gpus, ptrs.data(), gpu_stats[0].size()), "qlb_stats_allreduce");
     }
     else
         for (int g = 1; g < gpus; ++g)
-            for (size_t x = 0; x < sweep_stats[0].size(); ++x)
-                sweep_stats[0][x] += sweep_stats[g][x];
-    for (size_t pt = 0; pt < curr_sim; ++pt)
+            for (size_t x = 0; x < gpu_stats[0].size(); ++x)
+                gpu_stats[0][x] += gpu_stats[g][x];
+
+    // ---- results from the reduced integers ------------------------------------------------------------------------------------
+    size_t frames_total = 0, iterations_total = 0;
+    for (size_t pt = 0; pt < points_total; ++pt)
     {
-        const uint64_t *reduced = sweep_stats[0].data() + pt * stats_width;
-        if (reduced[max_it + 1] != point_ok_sp[pt] || reduced[max_it + 2] != point_ok_ldpc[pt] || reduced[max_it + 3] != trials)
-            throw std::runtime_error("reduced statistics disagree with the per-trial results");
-        g_report.points[pt].frame_iterations = reduced[max_it + 4];
+        const uint64_t *reduced = gpu_stats[0].data() + pt * stats_width;
+        if (reduced[max_it + 3] != trials)
+            throw std::runtime_error("reduced statistics do not account for every trial of point " + std::to_string(pt));
+        fill_result(sim_results[pt], point_stats_view{reduced, max_it}, trials);
+        g_report.points.push_back(report_of(pt, reduced[max_it + 4], point_seconds[pt]));
+        frames_total += trials;
         iterations_total += reduced[max_it + 4];
     }
-
-    g_report.seconds_total = std::chrono::duration<double>(clock::now() - t_start).count();
-    g_report.seconds_device = device_ns.load() * 1e-9 / workers;
-    g_report.seconds_startup = ready_ns.load() * 1e-9; // CUDA initialisation + contexts: ~1 s on a 1-GPU box, ~8 s on an 8-GPU box
+    if (progress_csv.is_open())
+    {
+        progress_csv.close();
+        progress_report.close();
+        std::error_code ec; // the caller writes the final files (write_file, write_report); the progress copies have served
+        fs::remove(progress_csv_path, ec);
+        fs::remove(progress_report_path, ec);
+    }
+    g_report.seconds_total = seconds_since(t_start);
+    g_report.seconds_device = device_seconds;
+    g_report.seconds_startup = startup_seconds; // CUDA initialisation + contexts: ~1 s on a 1-GPU box, ~7 s on an 8-GPU box
     g_report.frames = frames_total;
     g_report.frame_iterations = iterations_total;
     g_report.gpus = gpus;

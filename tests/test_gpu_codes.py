@@ -63,18 +63,12 @@ def test_large_block_length_matches_oracle(ctx, oracle):
                 assert (capi.unpack_bits(dec, n) == wdec).all()
 
 
-@pytest.mark.parametrize("form", ["split", "split_norepack", "persistent"])
-def test_streaming_kernel_equals_resident_kernel(ctx, oracle, form, monkeypatch):
+@pytest.mark.parametrize("norepack", [False, True])
+def test_streaming_kernel_equals_resident_kernel(ctx, oracle, norepack):
     """The frame-interleaved HBM-streaming decoder (forced with the tier-3 test hook) runs the same node arithmetic as the
     SM-resident kernel: iterations, flags and decoded keys must be identical, for a ragged batch (300 frames = 2 groups + 44)
-    mixing QBER points, in both fp32 rules. Both forms: one kernel per pass over all groups (the default) and the persistent
-    one-CTA-per-group kernel (QLB_STREAM_PERSISTENT, read by the library at launch time)."""
-    monkeypatch.delenv("QLB_STREAM_PERSISTENT", raising=False)
-    monkeypatch.delenv("QLB_SPLIT_NO_REPACK", raising=False)
-    if form == "persistent":
-        monkeypatch.setenv("QLB_STREAM_PERSISTENT", "1")
-    elif form == "split_norepack":  # without the frame-granular compaction (the mixed-QBER batch below triggers several repacks)
-        monkeypatch.setenv("QLB_SPLIT_NO_REPACK", "1")
+    mixing QBER points, in both fp32 rules -- with and without the on-device compaction of the live frames
+    (qlb_decode_params.stream_no_repack; the mixed-QBER batch below triggers several repacks)."""
     mat = codes.load_npz(codes.NORTH_STAR)
     code = capi.Code.from_graph(mat)
     seeds = oracle.trial_seeds(31337, 300)
@@ -86,7 +80,7 @@ def test_streaming_kernel_equals_resident_kernel(ctx, oracle, form, monkeypatch)
     A, B, Q = capi.pack_bits(np.stack(A)), capi.pack_bits(np.stack(B)), np.array(Q)
     for fast in (True, False):
         r = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=fast), A, B, Q, want_syndrome=True)
-        s = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=fast, tier=3), A, B, Q, want_syndrome=True)
+        s = ctx.reconcile_packed(code, capi.make_params(32, 60, 100.0, True, fast_math=fast, tier=3, stream_no_repack=norepack), A, B, Q, want_syndrome=True)
         assert (r[0] == s[0]).all(), np.flatnonzero(r[0] != s[0])
         assert (r[1] == s[1]).all() and (r[2] == s[2]).all() and (r[3] == s[3]).all()
     # and the sum-product entry (arbitrary LLRs + target syndromes) through the streaming kernel
@@ -138,7 +132,7 @@ def test_streaming_compaction_many_groups(ctx, oracle):
     assert (it_r == it_s).all() and (res_r == res_s).all() and (bits_r == bits_s).all()
 
 
-def test_streaming_decoder_in_waves(ctx, oracle, monkeypatch):
+def test_streaming_decoder_in_waves(ctx, oracle):
     """When device memory cannot hold every frame group the batch is decoded in waves (here forced: at most 2 bundles = 8 groups
     per wave for 2 500 frames = 20 groups -> 3 waves): per-wave state is re-used, frames are addressed through the wave's
     frame map. Must equal the resident kernel frame by frame."""
@@ -152,8 +146,7 @@ def test_streaming_decoder_in_waves(ctx, oracle, monkeypatch):
     perm = np.random.default_rng(11).permutation(len(Q))
     A, B, Q = np.ascontiguousarray(A[perm]), np.ascontiguousarray(B[perm]), Q[perm]
     r = ctx.reconcile_packed(code, capi.make_params(32, 50, 100.0, True, fast_math=True), A, B, Q, want_syndrome=True)
-    monkeypatch.setenv("QLB_SPLIT_MAX_BUNDLES", "2")
-    s = ctx.reconcile_packed(code, capi.make_params(32, 50, 100.0, True, fast_math=True, tier=3), A, B, Q, want_syndrome=True)
+    s = ctx.reconcile_packed(code, capi.make_params(32, 50, 100.0, True, fast_math=True, tier=3, stream_max_bundles=2), A, B, Q, want_syndrome=True)
     assert all((x == y).all() for x, y in zip(r, s))
 
 

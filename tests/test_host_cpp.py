@@ -165,17 +165,15 @@ def test_sweep_csv_equals_reference_dense_n7(sim, tmp_path):
     # a second run must not overwrite: the reference de-duplicates the file name
     run(sim, d)
     assert len(sorted((d / "results").glob("ldpc*.csv"))) == 2
+    assert not list((d / "results").glob("*.partial.csv")), "progress files are removed once the sweep has completed"
 
 
 @pytest.mark.gpu
-def test_sweep_fp32_and_forced_allreduce(sim, tmp_path, monkeypatch):
+def test_sweep_fp32_and_forced_allreduce(sim, tmp_path):
     """fp32 fast path through config.json (same FER / ratios on this grid; iteration means within a few percent), with the
-    NCCL statistics all-reduce forced on the single GPU."""
-    import os
-    d = make_dir(tmp_path, base_cfg(device_precision=32, device_fp32_fast_math=True), NS, False)
-    env = dict(os.environ, QKD_B200_FORCE_ALLREDUCE="1")
-    p = subprocess.run([str(sim), str(d)], capture_output=True, text=True, env=env)
-    assert p.returncode == 0, p.stderr
+    NCCL statistics all-reduce forced on the single GPU (config key device_force_allreduce)."""
+    d = make_dir(tmp_path, base_cfg(device_precision=32, device_fp32_fast_math=True, device_force_allreduce=True), NS, False)
+    run(sim, d)
     got = [ln.split(";") for ln in sorted((d / "results").glob("ldpc*.csv"))[0].read_text().splitlines()[1:]]
     want = [ln.split(";") for ln in (GOLD / "sweep_n10240_t64_seed777.csv").read_text().splitlines()[1:]]
     for g, w in zip(got, want):
