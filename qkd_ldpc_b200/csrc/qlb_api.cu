@@ -138,6 +138,23 @@ namespace
         if ((rc = upload(L.col_idx.data(), L.col_idx.size() * 4, dc, &p)))
             return rc;
         d.col_idx = static_cast<const int32_t *>(p);
+        {
+            std::vector<uint32_t> cg;
+            std::vector<uint16_t> bg;
+            uint32_t smem_slots = 0;
+            if (resident64_build_tables(ctx, d, L.bit_slots.data(), cg, bg, smem_slots))
+            {
+                if ((rc = upload(cg.data(), cg.size() * 4, dc, &p)))
+                    return rc;
+                d.r64_check_group_table = static_cast<const uint32_t *>(p);
+                if ((rc = upload(bg.data(), bg.size() * 2, dc, &p)))
+                    return rc;
+                d.r64_bit_group_table = static_cast<const uint16_t *>(p);
+                d.r64_check_groups = (int32_t)cg.size();
+                d.r64_bit_groups = (int32_t)bg.size();
+                d.r64_smem_slots = smem_slots;
+            }
+        }
         auto ins = ctx->codes.emplace(code->id, std::move(dc));
         *out = &ins.first->second.dev;
         return QLB_OK;
@@ -169,7 +186,7 @@ namespace
         typedef typename Math::real Real;
         auto kern = decode_kernel<Math, kTier, kReconcile, kShapeW, kThreads>;
         const Carve cv = make_carve<Real, kTier>(args.code.n, args.code.m, args.code.slots, args.code.max_bit_w);
-        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total_smem));
+        QLB_CUDA(allow_full_dynamic_smem(ctx, kern));
         int per_sm = 0;
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, cv.total_smem));
         if (per_sm < 1)
@@ -278,7 +295,7 @@ namespace
             while ((size_t)group * per_frame > budget)
                 group >>= 1;
         const size_t smem = stage ? (size_t)group * per_frame : 0;
-        QLB_CUDA(cudaFuncSetAttribute(syndrome_kernel<kSynThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        QLB_CUDA(allow_full_dynamic_smem(ctx, syndrome_kernel<kSynThreads>));
         const long long grid = (n_frames + group - 1) / group;
         syndrome_kernel<kSynThreads><<<(unsigned)grid, kSynThreads, smem, ctx->stream>>>(dev, n_frames, group, stage, d_bits, d_out);
         QLB_CUDA(cudaGetLastError());
@@ -926,7 +943,7 @@ extern "C"
         }
         auto launch = [&](auto kern, auto *state) -> int
         {
-            QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QLB_CUDA(allow_full_dynamic_smem(ctx, kern));
             for (int64_t f0 = 0; f0 < n_frames; f0 += slice)
             {
                 const int64_t nf = std::min(slice, n_frames - f0);

@@ -45,6 +45,27 @@ namespace qlb
             return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
         }
 
+        // e^-min(|m|, ~1024) for ANY double m, with the cap and the |.| made on the integer pipe (2 ALU instructions + one on the
+        // exponent) instead of the FP64 pipe's DADD / DSETP and two selects: the high word of |m| is limited to that of 1024.0
+        // (an infinity becomes 1024, a NaN some value in [1024, 1025): callers that can see a NaN track it themselves), and the
+        // binary exponent k is kept above -1000 so that the integer exponent insertion cannot wrap: beyond |m| ~ 693 the result is
+        // a positive number far below 2^-54 instead of e^-|m|, which is all tanh(|m| / 2) = (1 - e) / (1 + e) = 1 needs.
+        __device__ __forceinline__ double exp_neg_abs(double m)
+        {
+            const double kMagic = 6755399441055744.0;
+            const double a = __hiloint2double(min(__double2hiint(m) & 0x7fffffff, 0x40900000), __double2loint(m));
+            const double t = fma(-a, 1.4426950408889634, kMagic);
+            const int k = max(__double2loint(t), -1000);
+            const double kf = t - kMagic;
+            double r = fma(kf, -kLn2Hi, -a);
+            r = fma(kf, -kLn2Lo, r);
+            double p = kExp[13];
+#pragma unroll
+            for (int i = 12; i >= 0; --i)
+                p = fma(p, r, kExp[i]);
+            return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+        }
+
         // MUFU.RCP64H seed (relative error ~2^-20) and ONE Newton step: y = (1/d)(1 + eps), |eps| <~ 2^-40. Either sign of d.
         __device__ __forceinline__ double rcp_any(double d)
         {
@@ -104,13 +125,12 @@ namespace qlb
             return fma(dj, kLn2Hi, fma(2., s, fma(s, t2 + t1, dj * kLn2Lo)));
         }
 
-        // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped at 64 (the quotient is exactly +-1 far earlier).
+        // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped (exp_neg_abs; the quotient is exactly +-1 far earlier).
         // m = NaN comes back as +-1, NOT NaN: callers that can see a NaN message track it themselves (MathF64::check poisons the
         // row product, TwoPass<MathF64>::t passes the NaN through) so that the hot loop pays one compare instead of a select pair.
         __device__ __forceinline__ double tanh_half(double m)
         {
-            const double a = fabs(m);
-            const double e = exp_neg(-(a < 64. ? a : 64.));
+            const double e = exp_neg_abs(m);
             return copysign(div_any(1. - e, 1. + e), m);
         }
         // 2 atanh(p) = ln((1 + |p|) / (1 - |p|)) with p's sign, |p| <= 1 (the caller's p is a product of tanh values divided by one
@@ -118,14 +138,15 @@ namespace qlb
         // quotient of a <= d rounds to <= 1). ONE division serves the ratio and the logarithm (log_ratio). Edges: |p| = 1 gives
         // log_ratio(2, 0) = 1024 ln 2 -- finite, above any clamp the decoder can apply -- unless `want_inf`, the IEEE outcome +-inf
         // of the literal expression (needed only when the clamp is off); p = NaN gives NaN through the arithmetic itself.
-        __device__ __forceinline__ double two_atanh(double p, bool want_inf)
+        __device__ __forceinline__ double two_atanh_mag(double p, bool want_inf)
         {
             const double a = fabs(p);
             const double den = 1. - a;
             double r = log_ratio(1. + a, den);
             if (want_inf)
                 r = den == 0. ? __longlong_as_double(0x7ff0000000000000LL) : r;
-            return copysign(r, p);
+            return r; // >= 0 or NaN; the caller clamps the magnitude and then gives it p's sign
         }
+        __device__ __forceinline__ double two_atanh(double p, bool want_inf) { return copysign(two_atanh_mag(p, want_inf), p); }
     }
 }

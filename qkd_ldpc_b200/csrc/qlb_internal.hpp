@@ -81,6 +81,19 @@ struct qlb_ctx
 
 namespace qlb
 {
+    // Opt a kernel in to the device's whole per-block shared memory. ALWAYS the same value for a given kernel -- the attribute belongs
+    // to the function, not to the launch, and contexts are driven from several host threads at once: setting it to what the current
+    // launch needs lets another thread's smaller request land between this thread's set and its launch ("invalid argument").
+    template <typename Kernel>
+    inline cudaError_t allow_full_dynamic_smem(const qlb_ctx *ctx, Kernel kern)
+    {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess)
+            return e;
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)fa.sharedSizeBytes);
+    }
+
     // Block size (multiple of 32, in [max/2, max]) for the thread-per-node kernels. Every thread walks the bits with stride T and each
     // weight segment of the sorted checks with stride T, and the block waits for the slowest thread, so T is chosen to keep the
     // last round of each walk as full as possible (`check_share`: the check walk's share of an iteration); among equally balanced
@@ -122,5 +135,7 @@ namespace qlb
     bool stream_f32_eligible(const CodeDev &c);
     int launch_stream_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);
     bool resident_f64_eligible(const qlb_ctx *ctx, const CodeDev &c);
+    bool resident64_build_tables(const qlb_ctx *ctx, const CodeDev &c, const uint32_t *bit_slots, std::vector<uint32_t> &check_groups,
+                                 std::vector<uint16_t> &bit_groups, uint32_t &smem_slots);
     int launch_resident_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fused);
 }

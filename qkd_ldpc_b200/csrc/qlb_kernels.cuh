@@ -49,6 +49,11 @@ namespace qlb
         const uint32_t *check_order; // [m]
         const int32_t *row_ptr;      // [m+1]
         const int32_t *col_idx;      // [e]
+        // tables of the fp64 SM-resident kernel (qlb_resident_f64.cuh; null when the code or the device does not take it)
+        const uint32_t *r64_check_group_table; // [r64_check_groups]
+        const uint16_t *r64_bit_group_table;   // [r64_bit_groups]
+        int32_t r64_check_groups, r64_bit_groups;
+        uint32_t r64_smem_slots; // message slots kept in shared memory
     };
 
     struct DecodeArgs
@@ -118,10 +123,18 @@ namespace qlb
         static __device__ __forceinline__ double tanh_half(double m) { return f64m::tanh_half(m); }
         // |out| before the clamp; want_inf: the clamp is off, a saturated product must give inf (see f64m::two_atanh)
         static __device__ __forceinline__ double two_atanh(double p, bool want_inf) { return f64m::two_atanh(p, want_inf); }
+        // the clamp of :246-249 on the magnitude (NaN passes: the comparison is false), then p's sign: one FP64 compare per edge
+        static __device__ __forceinline__ double out(double p, bool en, double thr)
+        {
+            double r = f64m::two_atanh_mag(p, !en);
+            r = (en && r > thr) ? thr : r;
+            return copysign(r, p);
+        }
 #else
         static constexpr bool kOwnForms = false;
         static __device__ __forceinline__ double tanh_half(double m) { return tanh(m / 2.); }
         static __device__ __forceinline__ double two_atanh(double p, bool) { return 2. * atanh(p); }
+        static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(2. * atanh(p), thr, en); }
 #endif
         static __device__ __forceinline__ double quotient(double a, double d)
         {
@@ -150,7 +163,7 @@ namespace qlb
 #pragma unroll
             for (int k = 0; k < W; ++k)
                 if (k < w)
-                    v[k] = clamp_msg(two_atanh(quotient(row, v[k]), !en), thr, en);
+                    v[k] = out(quotient(row, v[k]), en, thr);
         }
     };
 
@@ -179,7 +192,7 @@ namespace qlb
                 {
                     poisoned |= v[k] != v[k];
                     neg ^= (int)((uint32_t)__double2hiint(v[k]) >> 31);
-                    e[k] = f64m::exp_neg(-fmin(fabs(v[k]), 64.));
+                    e[k] = f64m::exp_neg_abs(v[k]);
                     A *= 1. - e[k];
                     B *= 1. + e[k];
                 }
@@ -297,7 +310,7 @@ namespace qlb
             return (MathF64::kOwnForms && m != m) ? m : r; // tanh(NaN) = NaN (stored, then multiplied into the row product)
         }
         static __device__ __forceinline__ double quotient(double a, double d) { return MathF64::quotient(a, d); }
-        static __device__ __forceinline__ double out(double p, bool en, double thr) { return clamp_msg(MathF64::two_atanh(p, !en), thr, en); }
+        static __device__ __forceinline__ double out(double p, bool en, double thr) { return MathF64::out(p, en, thr); }
     };
     template <>
     struct TwoPass<MathF64Fused> : TwoPass<MathF64> // checks wider than the unrolled shapes keep the literal order

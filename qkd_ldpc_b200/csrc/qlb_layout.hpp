@@ -48,9 +48,18 @@ namespace qlb
 
         // Bank-aware placement. In the bit pass the 32 lanes of a warp (32 consecutive bits) gather one message each
         // through bit_slots[a][.]; with rows aligned to 32 slots the bank of a message is its check's sorted position mod
-        // 32. A random placement costs ~3.3 wavefronts per gather (balls in bins); re-ordering the checks inside each
-        // weight class so that the checks met by one warp at one list position fall into distinct banks brings that close
-        // to 1. Greedy placement followed by pairwise swaps that reduce sum(count^2) over (warp, position, bank).
+        // 32 (4-byte messages) and, for 8-byte messages -- which the hardware serves half-warp by half-warp over 16 pairs of
+        // banks -- its position mod 16 within the half-warp. A random placement costs ~3.3 wavefronts per 4-byte gather (balls
+        // in bins); re-ordering the checks inside each weight class so that the checks met by one warp at one list position
+        // fall into distinct banks brings that close to 1. Greedy placement followed by pairwise swaps that reduce
+        // sum(count^2) over (warp, position, bank mod 32) PLUS (warp, half-warp, position, bank mod 16): one order serves both
+        // message widths (lanes of one half-warp take one of {b, b + 16} for every b, the other half the complements).
+        //
+        // Inside a weight class the checks are first cut into kLastBitBuckets runs by the bit index of their LAST edge (the
+        // largest bit of the check for sorted adjacency lists), ascending, and the bank placement works inside a run. The fp64
+        // SM-resident kernel keeps the end of the last row of message slots outside shared memory: with this order those
+        // slots belong to bits of high index only, so that most 32-bit groups of its bit pass never leave shared memory.
+        static constexpr int kLastBitBuckets = 16;
         void spread_banks(const int32_t *rp, const int32_t *ci, const int32_t *cp, const std::vector<int32_t> &edge_of_bitslot)
         {
             const int32_t warps = (n + 31) / 32;
@@ -66,16 +75,18 @@ namespace qlb
                 {
                     const int32_t edge = edge_of_bitslot[q];
                     const int32_t j = static_cast<int32_t>(std::upper_bound(rp, rp + m + 1, edge) - rp) - 1;
-                    groups_of[j].push_back((i / 32) * max_bit_w + (q - cp[i]));
+                    groups_of[j].push_back(((i / 32) * max_bit_w + (q - cp[i])) * 2 + ((i % 32) / 16));
                 }
-            (void)ci;
-            std::vector<uint8_t> count(static_cast<size_t>(groups) * 32, 0);
+            // histograms per group: [32 banks] for 4-byte messages, then [2 half-warps][16 bank pairs] for 8-byte messages
+            std::vector<uint8_t> count(static_cast<size_t>(groups) * 64, 0);
+            auto idx32 = [](int32_t gh, int b) { return static_cast<size_t>(gh >> 1) * 64 + b; };
+            auto idx16 = [](int32_t gh, int b) { return static_cast<size_t>(gh >> 1) * 64 + 32 + (gh & 1) * 16 + (b & 15); };
             auto true_cost = [&](const std::vector<int32_t> &bank)
             {
                 std::vector<uint8_t> c(static_cast<size_t>(groups) * 32, 0);
                 for (int32_t j = 0; j < m; ++j)
                     for (int32_t g : groups_of[j])
-                        ++c[static_cast<size_t>(g) * 32 + bank[j]];
+                        ++c[static_cast<size_t>(g >> 1) * 32 + bank[j]];
                 double tot = 0;
                 int64_t used = 0;
                 for (int32_t g = 0; g < groups; ++g)
@@ -111,10 +122,20 @@ namespace qlb
             std::vector<uint32_t> new_order(m);
             while (lo < m)
             {
-                int32_t hi = lo;
+                // the next run: a kLastBitBuckets-th of a weight class (check_order is already sorted by (weight, last bit) here)
+                int32_t hi = lo, class_hi = lo;
                 const int32_t w = rp[check_order[lo] + 1] - rp[check_order[lo]];
-                while (hi < m && rp[check_order[hi] + 1] - rp[check_order[hi]] == w)
-                    ++hi;
+                while (class_hi < m && rp[check_order[class_hi] + 1] - rp[check_order[class_hi]] == w)
+                    ++class_hi;
+                {
+                    int32_t class_lo = lo;
+                    while (class_lo > 0 && rp[check_order[class_lo - 1] + 1] - rp[check_order[class_lo - 1]] == w)
+                        --class_lo;
+                    const int32_t run = std::max<int32_t>(64, (class_hi - class_lo + kLastBitBuckets - 1) / kLastBitBuckets);
+                    hi = std::min(class_hi, class_lo + ((lo - class_lo) / run + 1) * run);
+                    if (class_hi - hi < 64)
+                        hi = class_hi;
+                }
                 std::vector<int32_t> cap(32, 0);
                 for (int32_t p = lo; p < hi; ++p)
                     ++cap[p % 32];
@@ -130,7 +151,7 @@ namespace qlb
                             continue;
                         long c = 0;
                         for (int32_t g : groups_of[j])
-                            c += count[static_cast<size_t>(g) * 32 + b];
+                            c += count[idx32(g, b)] + count[idx16(g, b)];
                         if (best < 0 || c < best_cost)
                         {
                             best = b;
@@ -140,7 +161,10 @@ namespace qlb
                     bank[j] = best;
                     --cap[best];
                     for (int32_t g : groups_of[j])
-                        ++count[static_cast<size_t>(g) * 32 + best];
+                    {
+                        ++count[idx32(g, best)];
+                        ++count[idx16(g, best)];
+                    }
                 }
                 // pairwise swaps
                 const size_t sz = members.size();
@@ -151,8 +175,13 @@ namespace qlb
                         long d = 0;
                         for (int32_t g : groups_of[j])
                         {
-                            const long cf = count[static_cast<size_t>(g) * 32 + from], ct = count[static_cast<size_t>(g) * 32 + to];
+                            const long cf = count[idx32(g, from)], ct = count[idx32(g, to)];
                             d += (2 * ct + 1) - (2 * cf - 1); // (ct+1)^2 - ct^2 + (cf-1)^2 - cf^2
+                            if (((from ^ to) & 15) != 0)
+                            {
+                                const long hf = count[idx16(g, from)], ht = count[idx16(g, to)];
+                                d += (2 * ht + 1) - (2 * hf - 1);
+                            }
                         }
                         return d;
                     };
@@ -160,8 +189,10 @@ namespace qlb
                     {
                         for (int32_t g : groups_of[j])
                         {
-                            --count[static_cast<size_t>(g) * 32 + from];
-                            ++count[static_cast<size_t>(g) * 32 + to];
+                            --count[idx32(g, from)];
+                            ++count[idx32(g, to)];
+                            --count[idx16(g, from)];
+                            ++count[idx16(g, to)];
                         }
                         bank[j] = to;
                     };
@@ -282,8 +313,15 @@ namespace qlb
 
             check_order.resize(m);
             std::iota(check_order.begin(), check_order.end(), 0u);
+            // (large codes keep the file order inside a weight class: the streaming decoder wants the first edges of consecutive
+            // bits on consecutive message rows, and no SM-resident kernel takes them)
+            const bool by_last_bit = e < 65535;
+            auto last_bit = [&](uint32_t j) { return by_last_bit && rp[j + 1] > rp[j] ? ci[rp[j + 1] - 1] : 0; };
             std::stable_sort(check_order.begin(), check_order.end(), [&](uint32_t a, uint32_t b)
-                             { return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]); });
+                             {
+                                 const int32_t wa = rp[a + 1] - rp[a], wb = rp[b + 1] - rp[b];
+                                 return wa != wb ? wa > wb : last_bit(a) < last_bit(b);
+                             });
             spread_banks(rp, ci, cp, edge_of_bitslot);
             check_pos.resize(m);
             for (int32_t p = 0; p < m; ++p)

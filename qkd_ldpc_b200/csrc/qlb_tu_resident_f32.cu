@@ -15,7 +15,7 @@ namespace
             if (t >= 32 && t <= kResidentThreads && 32 * t >= args.code.n && 32 * t >= args.code.m)
                 kThreads = t;
         const size_t smem = resident_smem_bytes(args.code.n, args.code.m, args.code.slots, kBW);
-        QLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QLB_CUDA(allow_full_dynamic_smem(ctx, kern));
         long long grid = ctx->sm_count; // one resident CTA per SM
         if (grid > args.n_frames)
             grid = args.n_frames;

@@ -56,3 +56,37 @@ def make_frames(n: int, words: int, n_frames: int, q: float, seed: int, device, 
 
 def log_prior(q_exact: float) -> float:
     return math.log((1.0 - q_exact) / q_exact)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's trial seeds (src/simulation.cpp:222-228): seeds[k] = k-th raw output of Xoshiro256PlusPlus(simulation_seed)
+# (Reputeless/Xoshiro-cpp 1.1: state = four SplitMix64 outputs of the seed). Trial k of sweep point `pt` is seeded with
+# seeds[k] + pt (:247); fed to qlb_generate_device / qlb_run_trials these seeds re-create the reference's own frames bit for bit.
+_M64 = (1 << 64) - 1
+
+
+def _rotl(x: int, k: int) -> int:
+    return ((x << k) | (x >> (64 - k))) & _M64
+
+
+def trial_seeds(simulation_seed: int, count: int) -> np.ndarray:
+    x = int(simulation_seed) & _M64
+    s = []
+    for _ in range(4):  # SplitMix64
+        x = (x + 0x9E3779B97F4A7C15) & _M64
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        s.append(z ^ (z >> 31))
+    s0, s1, s2, s3 = s
+    out = np.empty(int(count), np.uint64)
+    for k in range(int(count)):
+        out[k] = (_rotl((s0 + s3) & _M64, 23) + s0) & _M64
+        t = (s1 << 17) & _M64
+        s2 ^= s0
+        s3 ^= s1
+        s1 ^= s2
+        s0 ^= s3
+        s2 ^= t
+        s3 = _rotl(s3, 45)
+    return out

@@ -167,3 +167,31 @@ def test_streaming_kernel_large_block_length(ctx, oracle):
             ok = want[:, 1] == 1
             assert (capi.unpack_bits(dec, n)[ok] == wdec[ok]).all()
             assert (np.abs(it.astype(int) - want[:, 0].astype(int)) <= 1).all()
+
+
+def test_block_length_one_million(ctx, oracle):
+    """BASELINE.json configs[3] at N = 1 000 000 (E = 3 000 000; seeded permutation code, codes.permutation_code): three frames --
+    two that converge (QBER 0.05, 8 rounds) and one that runs into max_it = 12 (QBER 0.10) -- against the fp64 oracle. fp64: the
+    large-frame fp64 decoder, iterations / flags / every decoded bit equal; fp32 (both rules): the streaming decoder, flags equal,
+    decoded key equal on the converged frames, iteration counts within one round. The device key generator runs at this length too."""
+    n, m = 1_000_000, 510_800
+    mat = codes.permutation_code(n, m, 3, 666)
+    g, code = graph_of(mat), capi.Code.from_graph(mat)
+    seeds = oracle.trial_seeds(99, 2)
+    for q, mi, sd in ((0.05, 12, seeds), (0.10, 12, seeds[:1])):
+        want, wdec = oracle.run_trials(g, q, sd, threads=2, max_it=mi, want_decoded=True)
+        A, B, Q = frames_for(oracle, n, q, sd)
+        ga, gb, gq = ctx.generate(n, sd, q)
+        assert gq == Q[0] and (capi.unpack_bits(ga, n) == A).all() and (capi.unpack_bits(gb, n) == B).all()
+        want_syn = np.stack([oracle.syndrome(g, a) for a in A])
+        for precision, fast in ((64, False), (64, True), (32, False), (32, True)):
+            it, res, dec, syn = ctx.reconcile_packed(code, capi.make_params(precision, mi, 100.0, True, fast_math=fast), ga, gb, Q, want_syndrome=True)
+            assert (capi.unpack_bits(syn, m) == want_syn).all()
+            assert ((res & 1) == want[:, 1]).all() and (((res >> 1) & 1) == want[:, 2]).all(), (q, precision, fast)
+            if precision == 64:
+                assert (it == want[:, 0]).all(), (q, fast, it, want[:, 0])
+                assert (capi.unpack_bits(dec, n) == wdec).all()
+            else:
+                ok = want[:, 1] == 1
+                assert (capi.unpack_bits(dec, n)[ok] == wdec[ok]).all()
+                assert (np.abs(it.astype(int) - want[:, 0].astype(int)) <= 1).all()

@@ -97,7 +97,7 @@ def test_layout_tables_north_star(matrices, dev_codes):
     cnt = np.array([(np.diff(mat.row_ptr) > k).sum() for k in range(code.max_check_w)])
     base = np.concatenate([[0], np.cumsum((cnt + 31) // 32 * 32)[:-1]])   # rows of slots start on 32-slot boundaries
     naive, placed = code.gather_wavefronts()
-    assert placed <= 0.7 * naive and placed <= 2.05, (naive, placed)          # bank-aware placement of the checks
+    assert placed <= 0.72 * naive and placed <= 2.1, (naive, placed)            # bank-aware placement of the checks (4- and 8-byte objective)
     for j in (0, 1, 700, mat.m - 1):
         for k, p in enumerate(range(mat.row_ptr[j], mat.row_ptr[j + 1])):
             assert slot_of_edge[p] == base[k] + pos[j]
