@@ -165,6 +165,38 @@ namespace qlb
                 if (k < w)
                     v[k] = out(quotient(row, v[k]), en, thr);
         }
+        // The same rule for a check of weight exactly W with the clamp folded into its operands: thr_eff = the clamp, or +inf
+        // when it is disabled (no magnitude exceeds it; a NaN fails the comparison and passes, :508-524); want_inf = the clamp is
+        // disabled or above ln(2^1024), i.e. a saturated product must come out as the IEEE infinity before the clamp.
+        template <int W>
+        static __device__ __forceinline__ void check_fast(double (&v)[W], bool s, double thr_eff, bool want_inf)
+        {
+#if !defined(QLB_F64_LIBM_FORMS)
+            double row = s ? -1. : 1.;
+            bool poisoned = false;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+            {
+                poisoned |= v[k] != v[k];
+                v[k] = tanh_half(v[k]);
+                row *= v[k];
+            }
+            row = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : row;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+            {
+                const double q = quotient(row, v[k]);
+                const double a = fabs(q), den = 1. - a;
+                double r = f64m::log_ratio(1. + a, den);
+                if (want_inf)
+                    r = den == 0. ? __longlong_as_double(0x7ff0000000000000LL) : r;
+                r = r > thr_eff ? thr_eff : r;
+                v[k] = copysign(r, q);
+            }
+#else
+            check<W>(v, W, s, thr_eff < __longlong_as_double(0x7ff0000000000000LL), thr_eff);
+#endif
+        }
     };
 
     // fp64, fused-ratio form of the same rule (QLB_FLAG_F64_FUSED_RATIO): with e_j = e^-|m_j|, tanh(|m_j|/2) = (1-e_j)/(1+e_j);
@@ -217,6 +249,39 @@ namespace qlb
                     const int sg = neg ^ (int)((uint32_t)__double2hiint(v[k]) >> 31);
                     v[k] = __hiloint2double(hi ^ (sg << 31), lo);
                 }
+        }
+        // Weight exactly W, clamp folded into thr_eff (see MathF64::check_fast). The regular case (den > 0) pays two FP64
+        // compares; everything else -- a saturated product, a zero or NaN message -- goes through one rarely-taken branch.
+        template <int W>
+        static __device__ __forceinline__ void check_fast(double (&v)[W], bool s, double thr_eff, bool)
+        {
+            double e[W];
+            double A = 1., B = 1.;
+            uint32_t neg = s ? 0x80000000u : 0u;
+            bool poisoned = false;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+            {
+                poisoned |= v[k] != v[k];
+                neg ^= (uint32_t)__double2hiint(v[k]);
+                e[k] = f64m::exp_neg_abs(v[k]);
+                A *= 1. - e[k];
+                B *= 1. + e[k];
+            }
+            const double S = B + A;
+            double D = B - A;
+            D = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : D; // a NaN input floods the check through the denominators
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+            {
+                const double num = fma(-e[k], D, S), den = fma(-e[k], S, D);
+                double r = f64m::log_ratio(num, den);
+                if (!(den > 0.)) // the IEEE outcomes of ln(num / den): +inf for a saturated product, NaN for 0 / 0 or a NaN
+                    r = (num > 0. && den <= 0.) ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff8000000000000LL);
+                r = r > thr_eff ? thr_eff : r;
+                const uint32_t sg = (neg ^ (uint32_t)__double2hiint(v[k])) & 0x80000000u;
+                v[k] = __hiloint2double((int)((uint32_t)__double2hiint(r) ^ sg), __double2loint(r));
+            }
         }
     };
 

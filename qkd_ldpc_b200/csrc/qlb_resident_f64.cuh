@@ -11,15 +11,17 @@
 //     high index only: ~85 % of the 32-bit groups of the bit pass never leave shared memory and run a loop without any
 //     shared / global predicate (`fast` groups); the others take the generic path.
 //
-// Schedule. Work is dealt to WARPS in groups of 32 consecutive nodes through a shared-memory counter (the slow groups first):
-// a warp that finishes early takes the next group, so the two block barriers of an iteration wait for one group at most,
-// not for the slowest of 24 fixed shares (ncu of the fixed-share version: 16 % of the time in those barriers). The tables
-// that describe the groups (built once per code and device by resident64_build_tables) sit in shared memory.
+// Schedule. Work is dealt to WARPS in groups of 32 consecutive nodes, round-robin over tables that list the slow groups (those
+// that reach into the global tail) first, so that every warp gets the same mix and whole groups only: the two block barriers
+// of an iteration wait for one group at most (the thread-strided walk of the first version left 16 % of the time in them,
+// ncu). Drawing the groups from a shared-memory counter was tried and dropped: the atomic's latency and the shorter prefetch
+// distance for the slot indices cost more than the balance returns. The tables (built once per code and device by
+// resident64_build_tables) sit in shared memory.
 //
 // Convergence (calculate_syndrome + arrays_equal after every bit pass, src/qkd_ldpc_algorithm.cpp:277-298) is tracked
 // INCREMENTALLY, in integers, exactly: s_unsat holds one bit per check, syndrome(z) ^ target. It is initialised once per
-// frame from the hard decision of the priors (a walk over the slot->bit table), and from then on a bit whose decision
-// flips in a bit pass toggles the bits of its checks. The frame has converged when the words are all zero -- known right
+// frame from the bit side -- every bit with Alice's bit != the prior's hard decision toggles the bits of its checks, as it
+// writes its prior into its message slots -- and from then on a bit whose decision flips in a bit pass does the same. The frame has converged when the words are all zero -- known right
 // after the bit pass, so a converged frame pays no speculative check pass, and the check pass itself carries nothing but
 // the check rule (bit-exact fp64 messages leave no spare mantissa bit to carry the decision as the fp32 kernel does).
 // Iteration counts, flags and keys follow the reference's definitions exactly (src/qkd_ldpc_algorithm.cpp:175-345,
@@ -29,7 +31,10 @@
 
 namespace qlb
 {
-    constexpr int kResident64Threads = 768; // launch bound (80 registers)
+#ifndef QLB_R64_THREADS
+#define QLB_R64_THREADS 768
+#endif
+    constexpr int kResident64Threads = QLB_R64_THREADS; // launch bound (768: 80 registers)
     constexpr int kResident64FastW = 8;     // weights up to this get the split-specialised loops
     constexpr size_t kResident64StaticSmem = 256;
 
@@ -65,12 +70,11 @@ namespace qlb
         return 2 * wn + 2 * wm + align_up((size_t)check_groups * 4, 16) + align_up((size_t)bit_groups * 2, 16);
     }
 
-    // The clamp of :313-316 (threshold_matrix: x > thr -> thr, x < -thr -> -thr, NaN untouched) with ONE FP64 compare.
-    __device__ __forceinline__ double clamp_f64(double x, double thr, bool en)
+    // The clamp of :313-316 (threshold_matrix: x > thr -> thr, x < -thr -> -thr, NaN untouched) with ONE FP64 compare; thr_eff is
+    // +inf when the clamp is disabled.
+    __device__ __forceinline__ double clamp_f64(double x, double thr_eff)
     {
-        if (en && fabs(x) > thr)
-            x = copysign(thr, x);
-        return x;
+        return fabs(x) > thr_eff ? copysign(thr_eff, x) : x;
     }
 
     struct Base64FromParams // constant-bank operands
@@ -86,7 +90,7 @@ namespace qlb
 
     // The check rule (:220-249) on the checks p0 + lane of one group.
     template <typename Math, int W, int kTail, typename Base>
-    __device__ __forceinline__ void check_group64(const Split64 &msg, const Base s_base, uint32_t p, bool active, bool syn, bool en, double thr)
+    __device__ __forceinline__ void check_group64(const Split64 &msg, const Base s_base, uint32_t p, bool active, bool syn, double thr_eff, bool want_inf)
     {
         if (!active)
             return;
@@ -98,7 +102,7 @@ namespace qlb
             const uint32_t slot = s_base(k) + p;
             v[k] = kTail == 3 ? msg.ld(slot) : (k < W - kTail ? msg.smem[slot] : gm[slot]);
         }
-        Math::template check<W>(v, W, syn, en, thr);
+        Math::template check_fast<W>(v, syn, thr_eff, want_inf);
 #pragma unroll
         for (int k = 0; k < W; ++k)
         {
@@ -114,9 +118,9 @@ namespace qlb
     // Weights 9..16 (the R >= 0.7 codes of the CW = 3 family) are kept out of line: their register appetite (2 x W doubles live) must
     // not leak into the hot instantiations; some spilling inside them is still far cheaper than the generic kernel's L2 round trips.
     template <typename Math, int W>
-    __device__ __noinline__ void check_group64_wide(const Split64 msg, const uint32_t *s_base, uint32_t p, bool active, bool syn, bool en, double thr)
+    __device__ __noinline__ void check_group64_wide(const Split64 msg, const uint32_t *s_base, uint32_t p, bool active, bool syn, double thr_eff, bool want_inf)
     {
-        check_group64<Math, W, 3>(msg, Base64FromSmem{s_base}, p, active, syn, en, thr);
+        check_group64<Math, W, 3>(msg, Base64FromSmem{s_base}, p, active, syn, thr_eff, want_inf);
     }
 
     // Sorted position of the check that owns `slot` (rows are laid out one edge position after the other, qlb_layout.hpp).
@@ -128,13 +132,9 @@ namespace qlb
         return slot - b;
     }
 
-    // Next group of a walk for this warp: lane 0 draws from the shared counter.
-    __device__ __forceinline__ int draw_group(int *counter, int lane)
+    __device__ __forceinline__ void toggle_bit(uint32_t *words, uint32_t p)
     {
-        int g = 0;
-        if (lane == 0)
-            g = atomicAdd(counter, 1);
-        return g;
+        asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(smem_u32(words + (p >> 5))), "r"(1u << (p & 31)) : "memory");
     }
 
     // kBW: uniform bit weight. Host-checked: slots < 65535, n < 65536, m < 65536, max_check_w <= 16, n % 32 == 0.
@@ -144,7 +144,6 @@ namespace qlb
         const int kThreads = blockDim.x; // multiple of 32, <= kMaxThreads
         extern __shared__ __align__(16) unsigned char smem[];
         __shared__ uint32_t s_base[kResidentMaxCW];
-        __shared__ int s_ctr[2]; // next group of the check walk / of the bit walk
         __shared__ long long s_frame;
 
         const CodeDev &code = args.code;
@@ -153,6 +152,7 @@ namespace qlb
         const size_t wn = align_up((size_t)words_n * 4, 16), wm = align_up((size_t)words_m * 4, 16);
         const int n_cg = code.r64_check_groups, n_bg = code.r64_bit_groups;
         const uint32_t smem_slots = code.r64_smem_slots;
+        (void)m;
 
         Split64 msg;
         msg.smem = reinterpret_cast<double *>(smem);
@@ -165,9 +165,6 @@ namespace qlb
         uint32_t *s_unsat = reinterpret_cast<uint32_t *>(tail + 2 * wn + wm);  // syndrome(z) ^ target, sorted check order
         uint32_t *s_cg = reinterpret_cast<uint32_t *>(tail + 2 * wn + 2 * wm);
         uint16_t *s_bg = reinterpret_cast<uint16_t *>(tail + 2 * wn + 2 * wm + align_up((size_t)n_cg * 4, 16));
-        // frame set-up only, before the messages are written: Alice's key and the syndrome in natural check order
-        uint32_t *t_alice = reinterpret_cast<uint32_t *>(smem);
-        uint32_t *t_synn = reinterpret_cast<uint32_t *>(smem + wn);
 
         if (tid < kResidentMaxCW)
             s_base[tid] = code.base[tid];
@@ -176,9 +173,9 @@ namespace qlb
         for (int g = tid; g < n_bg; g += kThreads)
             s_bg[g] = code.r64_bit_group_table[g];
         const uint16_t *bslot = code.bit_slots16;
-        const uint16_t *col_of_slot = code.col_of_slot16;
-        const bool en = args.enable_thr != 0;
-        const double thr = args.thr;
+        const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+        const double thr_eff = args.enable_thr ? args.thr : kInf; // the clamp as an operand: nothing exceeds +inf
+        const bool want_inf = !(thr_eff <= 700.);                  // a saturated product must be the IEEE infinity before the clamp
 
         for (;;)
         {
@@ -190,135 +187,112 @@ namespace qlb
             if (f >= args.n_frames)
                 break;
 
-            // ---- A: keys / target syndrome into shared memory; z0 = the priors' own hard decision ---------------------------
+            // ---- A: Bob's key / the target syndrome into shared memory -----------------------------------------------------
             double lp = 0.;
             const double *llr_f = nullptr;
             if (kReconcile)
             {
                 lp = args.log_prior[f];
                 for (int w = tid; w < words_n; w += kThreads)
-                {
                     s_bob[w] = args.bob[f * words_n + w];
-                    t_alice[w] = args.alice[f * words_n + w];
-                }
                 for (int w = tid; w < words_m; w += kThreads)
-                    t_synn[w] = 0;
+                    s_syn[w] = s_unsat[w] = 0;
             }
             else
             {
                 llr_f = args.llr + f * n;
-                for (int w = tid; w < words_m; w += kThreads)
-                    t_synn[w] = args.syndrome_in[f * words_m + w];
-            }
-            for (int w = tid; w < words_m; w += kThreads)
-            {
-                s_unsat[w] = 0;
-                s_syn[w] = 0;
-            }
-            __syncthreads();
-            for (int g = warp; g < words_n; g += warps) // n % 32 == 0: whole warps only
-            {
-                const int i = g * 32 + lane;
-                double prior;
-                if (kReconcile)
-                    prior = ((s_bob[g] >> lane) & 1u) ? -lp : lp; // :401-405
-                else
-                    prior = llr_f[i];
-                const uint32_t word = __ballot_sync(0xffffffffu, prior <= 0.);
-                if (lane == 0)
-                    s_z[g] = word;
-            }
-            __syncthreads();
-            // ---- B: one walk over the checks through the slot -> bit table: the target syndrome (reconcile mode: Alice's
-            // syndrome, :413-414) and s_unsat <- syndrome(z0) ^ target, both in sorted check order ---------------------------
-            for (int g = warp; g < n_cg; g += warps)
-            {
-                const uint32_t ent = s_cg[g];
-                const uint32_t p = ((ent & 0x7ffu) << 5) + lane;
-                const bool active = lane >= (int)((ent >> 11) & 31u) && lane <= (int)((ent >> 16) & 31u);
-                const int w = (int)(ent >> 23);
-                uint32_t sb = 0, pz = 0;
-                if (active)
+                // target syndrome (natural check order in the API) -> sorted order; s_unsat starts as the target and is toggled by z0 below
+                for (int g = warp; g < words_m; g += warps)
                 {
-                    uint32_t pa = 0;
-                    for (int k = 0; k < w; ++k)
+                    const int p = g * 32 + lane;
+                    uint32_t sb = 0;
+                    if (p < m)
                     {
-                        const uint32_t col = col_of_slot[s_base[k] + p];
-                        pz ^= s_z[col >> 5] >> (col & 31);
-                        if (kReconcile)
-                            pa ^= t_alice[col >> 5] >> (col & 31);
+                        const uint32_t j = code.check_order[p];
+                        sb = (args.syndrome_in[f * words_m + (j >> 5)] >> (j & 31)) & 1u;
                     }
-                    const uint32_t j = code.check_order[p];
-                    if (kReconcile)
-                    {
-                        sb = pa & 1u;
-                        if (sb && args.syndrome_out)
-                            atomicOr(&t_synn[j >> 5], 1u << (j & 31));
-                    }
-                    else
-                        sb = (t_synn[j >> 5] >> (j & 31)) & 1u;
-                }
-                const uint32_t syn_word = __ballot_sync(0xffffffffu, active && sb);
-                const uint32_t unsat_word = __ballot_sync(0xffffffffu, active && ((sb ^ pz) & 1u));
-                if (lane == 0) // two groups can share a word (a weight class ending inside it)
-                {
-                    if (syn_word)
-                        atomicOr(&s_syn[p >> 5], syn_word);
-                    if (unsat_word)
-                        atomicOr(&s_unsat[p >> 5], unsat_word);
+                    const uint32_t word = __ballot_sync(0xffffffffu, sb);
+                    if (lane == 0)
+                        s_syn[g] = s_unsat[g] = word;
                 }
             }
             __syncthreads();
-            if (kReconcile && args.syndrome_out)
+            // ---- B: messages <- priors, unclamped (:182-190); z0 = the priors' own hard decision; the target syndrome (reconcile
+            // mode: Alice's syndrome, :413-414) and s_unsat = syndrome(z0) ^ target from the BIT side: a bit toggles the bits of its
+            // checks (a few thousand shared-memory reductions, no dependent walk over the checks' edge lists) -------------------------
             {
-                for (int w = tid; w < words_m; w += kThreads)
-                    args.syndrome_out[f * words_m + w] = t_synn[w];
-                __syncthreads();
-            }
-            // ---- C: messages <- priors, unclamped (:182-190) -----------------------------------------------------------------
-            for (int g = warp; g < words_n; g += warps)
-            {
-                const int i = g * 32 + lane;
-                double prior;
-                if (kReconcile)
-                    prior = ((s_bob[g] >> lane) & 1u) ? -lp : lp;
-                else
-                    prior = llr_f[i];
+                // the Alice words of this warp's groups (group warp + l * warps in lane l), fetched in one go
+                uint32_t my_alice = 0;
+                int r = 0;
+                for (int g = warp; g < words_n; g += warps, ++r) // n % 32 == 0: whole warps only
+                {
+                    if (kReconcile && (r & 31) == 0)
+                        my_alice = warp + (r + lane) * warps < words_n ? args.alice[f * words_n + warp + (r + lane) * warps] : 0u;
+                    const int i = g * 32 + lane;
+                    uint32_t sl[kBW];
 #pragma unroll
-                for (int a = 0; a < kBW; ++a)
-                    msg.st(bslot[a * n + i], prior);
+                    for (int a = 0; a < kBW; ++a)
+                        sl[a] = bslot[a * n + i];
+                    double prior;
+                    if (kReconcile)
+                        prior = __hiloint2double(__double2hiint(lp) ^ (int)(((s_bob[g] >> lane) & 1u) << 31), __double2loint(lp)); // :401-405
+                    else
+                        prior = llr_f[i];
+                    const bool z0 = prior <= 0.;
+                    const uint32_t word = __ballot_sync(0xffffffffu, z0);
+                    if (lane == 0)
+                        s_z[g] = word;
+                    const bool ab = kReconcile && ((__shfl_sync(0xffffffffu, my_alice, r & 31) >> lane) & 1u);
+#pragma unroll
+                    for (int a = 0; a < kBW; ++a)
+                    {
+                        msg.st(sl[a], prior);
+                        if (ab || z0)
+                        {
+                            const uint32_t p = check_of_slot64(sl[a], s_base, code.max_check_w);
+                            if (ab)
+                                toggle_bit(s_syn, p);
+                            if (ab != z0)
+                                toggle_bit(s_unsat, p);
+                        }
+                    }
+                }
             }
-            if (tid == 0)
-                s_ctr[0] = 0;
             __syncthreads();
+            if (kReconcile && args.syndrome_out) // Alice's syndrome in natural check order
+            {
+                for (int w = tid; w < words_m; w += kThreads)
+                    args.syndrome_out[f * words_m + w] = 0;
+                __syncthreads();
+                for (int p = tid; p < m; p += kThreads)
+                    if ((s_syn[p >> 5] >> (p & 31)) & 1u)
+                    {
+                        const uint32_t j = code.check_order[p];
+                        atomicOr(&args.syndrome_out[f * words_m + (j >> 5)], 1u << (j & 31));
+                    }
+            }
 
             int it = 0; // completed bit passes
             bool success = false;
             while (it < args.max_it)
             {
                 // ---- check pass (:220-249) -----------------------------------------------------------------------------------
-                if (tid == 0)
-                    s_ctr[1] = 0; // every warp has left the previous bit pass
                 {
-                    int nxt = draw_group(&s_ctr[0], lane);
-                    for (;;)
+#pragma unroll 1
+                    for (int g = warp; g < n_cg; g += warps)
                     {
-                        const int g = __shfl_sync(0xffffffffu, nxt, 0);
-                        if (g >= n_cg)
-                            break;
-                        nxt = draw_group(&s_ctr[0], lane);
                         const uint32_t ent = s_cg[g];
                         const uint32_t p = ((ent & 0x7ffu) << 5) + lane;
                         const bool active = lane >= (int)((ent >> 11) & 31u) && lane <= (int)((ent >> 16) & 31u);
                         const bool syn = ((s_syn[ent & 0x7ffu] >> lane) & 1u) != 0;
                         switch (ent >> 21)
                         {
-#define QLB_GRP64(W_)                                                                                            \
-    case W_ * 4 + 0: check_group64<Math, W_, 0>(msg, Base64FromParams{args}, p, active, syn, en, thr); break;     \
-    case W_ * 4 + 1: check_group64<Math, W_, 1>(msg, Base64FromParams{args}, p, active, syn, en, thr); break;     \
-    case W_ * 4 + 3: check_group64<Math, W_, 3>(msg, Base64FromParams{args}, p, active, syn, en, thr); break;
+#define QLB_GRP64(W_)                                                                                                       \
+    case W_ * 4 + 0: check_group64<Math, W_, 0>(msg, Base64FromParams{args}, p, active, syn, thr_eff, want_inf); break;     \
+    case W_ * 4 + 1: check_group64<Math, W_, 1>(msg, Base64FromParams{args}, p, active, syn, thr_eff, want_inf); break;     \
+    case W_ * 4 + 3: check_group64<Math, W_, 3>(msg, Base64FromParams{args}, p, active, syn, thr_eff, want_inf); break;
 #define QLB_GRP64W(W_) \
-    case W_ * 4 + 3: check_group64_wide<Math, W_>(msg, s_base, p, active, syn, en, thr); break;
+    case W_ * 4 + 3: check_group64_wide<Math, W_>(msg, s_base, p, active, syn, thr_eff, want_inf); break;
                             QLB_GRP64(1) QLB_GRP64(2) QLB_GRP64(3) QLB_GRP64(4) QLB_GRP64(5) QLB_GRP64(6) QLB_GRP64(7) QLB_GRP64(8)
                             QLB_GRP64W(9) QLB_GRP64W(10) QLB_GRP64W(11) QLB_GRP64W(12) QLB_GRP64W(13) QLB_GRP64W(14) QLB_GRP64W(15) QLB_GRP64W(16)
 #undef QLB_GRP64
@@ -331,40 +305,29 @@ namespace qlb
                 __syncthreads();
                 // ---- bit pass: total (:256-258), decision (:259-266), extrinsic + clamp (:300-316); a flipped decision toggles
                 // the unsatisfied-bits of the bit's checks ------------------------------------------------------------------
-                if (tid == 0)
-                    s_ctr[0] = 0; // every warp has left the check pass
                 {
-                    int nxt = draw_group(&s_ctr[1], lane);
-                    int g = __shfl_sync(0xffffffffu, nxt, 0);
-                    uint32_t ent = 0, sl[kBW];
-                    if (g < n_bg)
-                    {
-                        ent = s_bg[g];
-                        nxt = draw_group(&s_ctr[1], lane);
+                    // this warp's groups: entries warp, warp + warps, ... of the table (slow groups first, so every warp gets its
+                    // share of them); the slot indices (L2) of the group after next travel while a group is processed
+                    uint32_t ent = warp < n_bg ? s_bg[warp] : 0u, ent1 = warp + warps < n_bg ? s_bg[warp + warps] : 0u;
+                    uint32_t sl[kBW], sl1[kBW];
 #pragma unroll
-                        for (int a = 0; a < kBW; ++a)
-                            sl[a] = bslot[a * n + (int)(ent & 0x7fffu) * 32 + lane];
+                    for (int a = 0; a < kBW; ++a)
+                    {
+                        sl[a] = bslot[a * n + (int)(ent & 0x7fffu) * 32 + lane];
+                        sl1[a] = bslot[a * n + (int)(ent1 & 0x7fffu) * 32 + lane];
                     }
-                    while (g < n_bg)
+#pragma unroll 1
+                    for (int g = warp; g < n_bg; g += warps)
                     {
-                        // the next group's slot indices (L2) travel while this group's messages are gathered
-                        const int g2 = __shfl_sync(0xffffffffu, nxt, 0);
-                        uint32_t ent2 = 0, sl2[kBW];
+                        const uint32_t ent2 = g + 2 * warps < n_bg ? s_bg[g + 2 * warps] : 0u;
+                        uint32_t sl2[kBW];
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
-                            sl2[a] = 0;
-                        if (g2 < n_bg)
-                        {
-                            ent2 = s_bg[g2];
-                            nxt = draw_group(&s_ctr[1], lane);
-#pragma unroll
-                            for (int a = 0; a < kBW; ++a)
-                                sl2[a] = bslot[a * n + (int)(ent2 & 0x7fffu) * 32 + lane];
-                        }
+                            sl2[a] = bslot[a * n + (int)(ent2 & 0x7fffu) * 32 + lane];
                         const int grp = (int)(ent & 0x7fffu);
                         double prior;
                         if (kReconcile)
-                            prior = ((s_bob[grp] >> lane) & 1u) ? -lp : lp;
+                            prior = __hiloint2double(__double2hiint(lp) ^ (int)(((s_bob[grp] >> lane) & 1u) << 31), __double2loint(lp));
                         else
                             prior = llr_f[grp * 32 + lane];
                         double c[kBW];
@@ -381,7 +344,7 @@ namespace qlb
                             z = total <= 0.;
 #pragma unroll
                             for (int a = 0; a < kBW; ++a)
-                                msg.smem[sl[a]] = clamp_f64(total - c[a], thr, en);
+                                msg.smem[sl[a]] = clamp_f64(total - c[a], thr_eff);
                         }
                         else
                         {
@@ -395,27 +358,30 @@ namespace qlb
                             z = total <= 0.;
 #pragma unroll
                             for (int a = 0; a < kBW; ++a)
-                                msg.st(sl[a], clamp_f64(total - c[a], thr, en));
+                                msg.st(sl[a], clamp_f64(total - c[a], thr_eff));
                         }
                         const uint32_t word = __ballot_sync(0xffffffffu, z);
                         const uint32_t flips = word ^ s_z[grp];
-                        if ((flips >> lane) & 1u)
+                        if (flips) // warp-uniform
                         {
-#pragma unroll 1
-                            for (int a = 0; a < kBW; ++a)
+                            if ((flips >> lane) & 1u)
                             {
-                                const uint32_t p = check_of_slot64(sl[a], s_base, code.max_check_w);
-                                atomicXor(&s_unsat[p >> 5], 1u << (p & 31));
+#pragma unroll 1
+                                for (int a = 0; a < kBW; ++a)
+                                    toggle_bit(s_unsat, check_of_slot64(sl[a], s_base, code.max_check_w));
                             }
+                            __syncwarp();
+                            if (lane == 0)
+                                s_z[grp] = word;
                         }
-                        __syncwarp();
-                        if (lane == 0 && flips)
-                            s_z[grp] = word;
-                        g = g2;
-                        ent = ent2;
+                        ent = ent1;
+                        ent1 = ent2;
 #pragma unroll
                         for (int a = 0; a < kBW; ++a)
-                            sl[a] = sl2[a];
+                        {
+                            sl[a] = sl1[a];
+                            sl1[a] = sl2[a];
+                        }
                     }
                 }
                 ++it;

@@ -62,9 +62,11 @@ namespace
     {
         switch (args.code.uniform_bit_w)
         {
+#ifndef QLB_R64_LEAN // kernel-tuning builds (scripts/build_stream_variants.py) compile the bit weight of the benchmark code only
         case 2: return launch_resident64<Math, kReconcile, 2>(ctx, args);
-        case 3: return launch_resident64<Math, kReconcile, 3>(ctx, args);
         case 4: return launch_resident64<Math, kReconcile, 4>(ctx, args);
+#endif
+        case 3: return launch_resident64<Math, kReconcile, 3>(ctx, args);
         default: return fail(QLB_ERR_UNSUPPORTED, "fp64 resident kernel: unsupported bit weight");
         }
     }

@@ -7,7 +7,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from qkd_ldpc_b200 import build as b
 
-TU = "qlb_tu_stream_f32.cu"
+TU = "qlb_tu_stream.cu"
 if len(sys.argv) > 2 and sys.argv[1] == "--tu":
     TU = sys.argv[2]
     del sys.argv[1:3]
