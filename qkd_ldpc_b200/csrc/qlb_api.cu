@@ -129,6 +129,9 @@ namespace
                 return rc;
             d.col_of_slot16 = static_cast<const uint16_t *>(p);
         }
+        if ((rc = upload(L.col_of_slot.data(), L.col_of_slot.size() * 4, dc, &p)))
+            return rc;
+        d.col_of_slot32 = static_cast<const uint32_t *>(p);
         if ((rc = upload(L.check_order.data(), L.check_order.size() * 4, dc, &p)))
             return rc;
         d.check_order = static_cast<const uint32_t *>(p);
@@ -267,12 +270,15 @@ namespace
         if (p->precision == QLB_PRECISION_F32 && forced < 0 && resident_f32_eligible(ctx, args.code))
             return launch_resident_f32(ctx, args, kReconcile, fast);
         // codes too large for one SM's shared memory: frame-interleaved streaming through HBM (test hook: tier 3 forces it)
-        if (p->precision == QLB_PRECISION_F32 && (forced < 0 || forced == 3) && stream_f32_eligible(args.code))
+        if (p->precision == QLB_PRECISION_F32 && (forced < 0 || forced == 3) && stream_eligible(args.code))
             return launch_stream_f32(ctx, args, kReconcile, fast);
-        if (forced == 3)
-            return fail(QLB_ERR_UNSUPPORTED, "the streaming kernel does not handle this code / precision");
         if (p->precision == QLB_PRECISION_F64 && forced < 0 && resident_f64_eligible(ctx, args.code))
             return launch_resident_f64(ctx, args, kReconcile, (p->flags & QLB_FLAG_F64_FUSED_RATIO) != 0);
+        // fp64 at block lengths whose indices do not fit the generic kernel's shared-memory tiers: the fp64 streaming decoder
+        if (p->precision == QLB_PRECISION_F64 && (forced == 3 || (forced < 0 && args.code.slots >= 65535)) && stream_eligible(args.code))
+            return launch_stream_f64(ctx, args, kReconcile, (p->flags & QLB_FLAG_F64_FUSED_RATIO) != 0);
+        if (forced == 3)
+            return fail(QLB_ERR_UNSUPPORTED, "the streaming kernel does not handle this code / precision");
         if (p->precision == QLB_PRECISION_F64)
             return (p->flags & QLB_FLAG_F64_FUSED_RATIO) ? launch_tier<MathF64Fused, kReconcile>(ctx, args, forced)
                                                          : launch_tier<MathF64, kReconcile>(ctx, args, forced);

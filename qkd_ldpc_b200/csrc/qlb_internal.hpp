@@ -132,8 +132,9 @@ namespace qlb
     // launchers of the specialised decoders (each in its own TU); `fast`: the SFU check rule
     bool resident_f32_eligible(const qlb_ctx *ctx, const CodeDev &c);
     int launch_resident_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);
-    bool stream_f32_eligible(const CodeDev &c);
+    bool stream_eligible(const CodeDev &c);
     int launch_stream_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast);
+    int launch_stream_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fused); // `fused`: the fused-ratio check rule
     bool resident_f64_eligible(const qlb_ctx *ctx, const CodeDev &c);
     bool resident64_build_tables(const qlb_ctx *ctx, const CodeDev &c, const uint32_t *bit_slots, std::vector<uint32_t> &check_groups,
                                  std::vector<uint16_t> &bit_groups, uint32_t &smem_slots);

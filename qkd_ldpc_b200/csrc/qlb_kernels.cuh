@@ -46,6 +46,7 @@ namespace qlb
         const uint16_t *bit_slots16; // [max_bit_w][n] (0xFFFF = none), valid when e < 65535
         const uint32_t *bit_slots32; // [max_bit_w][n] (0xFFFFFFFF = none)
         const uint16_t *col_of_slot16; // [slots] bit index of the edge stored at a slot, valid when n < 65536
+        const uint32_t *col_of_slot32; // [slots] the same, any n (0xFFFFFFFF = padding slot)
         const uint32_t *check_order; // [m]
         const int32_t *row_ptr;      // [m+1]
         const int32_t *col_idx;      // [e]

@@ -1,26 +1,50 @@
-// Shared pieces of the fp32 frame-interleaved "streaming" decoder (qlb_stream_split.cuh): the kernels for codes whose
+// Shared pieces of the frame-interleaved "streaming" decoder (qlb_stream_split.cuh), fp32 and fp64: the kernels for codes whose
 // messages do not fit in shared memory (BASELINE.json configs[3]: N = 100 000 ... 1 000 000) -- the HBM-bound design point
 // of SURVEY.md 8d.
 //
-// Frames are decoded in GROUPS of G = 32 * VEC (VEC = 4: 128-bit accesses). Messages are stored slot-major, frame-minor:
-// msg[slot][G]. A WARP works on one node at a time and lane l owns frames VEC*l ... VEC*l+VEC-1 of the group, so whatever
-// the Tanner graph looks like, every message access of the warp is one fully coalesced row of G floats (512 B for VEC = 4),
+// Frames are decoded in GROUPS of G = 32 * VEC (128-bit accesses: VEC = 4 floats or 2 doubles). Messages are stored slot-major,
+// frame-minor: msg[slot][G]. A WARP works on one node at a time and lane l owns frames VEC*l ... VEC*l+VEC-1 of the group, so
+// whatever the Tanner graph looks like, every message access of the warp is one fully coalesced 512-byte row,
 // and the graph indices are warp-uniform (one broadcast load per node, amortised over the G frames). Traffic per executed
-// iteration is the algorithmic 16 B per edge and frame (read + write in the check pass, read + write in the bit pass) plus
-// < 2 % of indices and packed bits. Keys, decisions and syndromes are kept bit-transposed per group ([node][VEC] words, word j
-// bit l = frame VEC*l + j) so a lane extracts its frames' bits with one shift; the transposes run once per group with
-// __ballot_sync. Node arithmetic, the decision-in-LSB trick and the convergence rule are those of the SM-resident kernel
-// (qlb_resident_f32.cuh); a converged frame is frozen (decisions and counters kept) while its group finishes.
+// iteration is the algorithmic 16 B (fp32) / 32 B (fp64) per edge and frame (read + write in the check pass, read + write in the
+// bit pass) plus < 3 % of indices and packed bits. Keys, decisions and syndromes are kept bit-transposed per group ([node][VEC]
+// words, word j bit l = frame VEC*l + j) so a lane extracts its frames' bits with one shift; the transposes run once per group
+// with __ballot_sync. fp32: node arithmetic, the decision-in-LSB trick and the convergence rule are those of the SM-resident
+// kernel (qlb_resident_f32.cuh). fp64: the reference's arithmetic and order (MathF64 / MathF64Fused::check_fast, the bit rule of
+// qlb_resident_f64.cuh); its messages have no spare mantissa bit, so a check's parity comes from the packed decisions of its
+// bits (slot -> bit table + one warp-uniform word per bit and frame word). A converged frame is frozen (decisions and counters
+// kept) while its group finishes.
 #pragma once
 #include "qlb_resident_f32.cuh"
+#include "qlb_resident_f64.cuh"
 
 namespace qlb
 {
 
-    template <int VEC>
+    // How a precision rides through the streaming kernels: the message type, the widest group (128-bit accesses), whether the
+    // bit's hard decision travels in the mantissa LSB of its outgoing messages (fp32: the bar is statistical) or is read from
+    // the packed decisions (fp64: outcome-exact).
+    template <typename Rule_>
+    struct StreamF32
+    {
+        typedef float real;
+        typedef Rule_ Rule;
+        static constexpr bool kLsbDecision = true;
+        static constexpr int kVecWide = 4;
+    };
+    template <typename Math_>
+    struct StreamF64
+    {
+        typedef double real;
+        typedef Math_ Math;
+        static constexpr bool kLsbDecision = false;
+        static constexpr int kVecWide = 2;
+    };
+
+    template <typename Real, int VEC>
     struct VecIO;
     template <>
-    struct VecIO<4>
+    struct VecIO<float, 4>
     {
         static __device__ __forceinline__ void load(const float *p, float (&v)[4])
         {
@@ -41,10 +65,20 @@ namespace qlb
         }
     };
     template <>
-    struct VecIO<1>
+    struct VecIO<double, 2>
     {
-        static __device__ __forceinline__ void load(const float *p, float (&v)[1]) { v[0] = *p; }
-        static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
+        static __device__ __forceinline__ void load(const double *p, double (&v)[2])
+        {
+            const double2 t = *reinterpret_cast<const double2 *>(p);
+            v[0] = t.x; v[1] = t.y;
+        }
+        static __device__ __forceinline__ void store(double *p, const double (&v)[2]) { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
+    };
+    template <typename Real>
+    struct VecIO<Real, 1>
+    {
+        static __device__ __forceinline__ void load(const Real *p, Real (&v)[1]) { v[0] = *p; }
+        static __device__ __forceinline__ void store(Real *p, const Real (&v)[1]) { *p = v[0]; }
     };
 
     // Software prefetch into L2: registers bound how many demand loads a warp can keep in flight (W rows of 512 B), which is
@@ -84,7 +118,7 @@ namespace qlb
         {
             row[k] = msg + ((size_t)(code.base[k] + p) * row_stride + VEC * lane);
             float t[VEC];
-            VecIO<VEC>::load(row[k], t);
+            VecIO<float, VEC>::load(row[k], t);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
                 v[j][k] = t[j];
@@ -123,7 +157,63 @@ namespace qlb
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
                 t[j] = v[j][k];
-            VecIO<VEC>::store(row[k], t);
+            VecIO<float, VEC>::store(row[k], t);
+        }
+    }
+
+    // fp64: one check of weight exactly W for the VEC frames of this lane, the reference's rule (Math::check_fast). bitsT: the
+    // bit-transposed words the check's parity is formed from -- Alice's key in the first pass of a reconciliation (the parity IS
+    // her syndrome bit, src/qkd_ldpc_algorithm.cpp:413-414), the decisions of the last bit pass afterwards (:277-298).
+    template <typename Math, int W, int VEC>
+    __device__ __forceinline__ void stream_check64(double *__restrict__ msg, const CodeDev &code, uint32_t p, int lane, uint32_t *__restrict__ synT,
+                                                   const uint32_t *__restrict__ bitsT, double thr_eff, bool want_inf, bool first, uint32_t (&bad)[VEC],
+                                                   size_t row_stride)
+    {
+        double v[VEC][W];
+        double *row[W];
+        uint32_t par[VEC], synw[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+            par[j] = 0;
+            synw[j] = first ? 0u : synT[(size_t)p * VEC + j];
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+        {
+            row[k] = msg + ((size_t)(code.base[k] + p) * row_stride + VEC * lane);
+            double t[VEC];
+            VecIO<double, VEC>::load(row[k], t);
+            const uint32_t bit = code.col_of_slot32[code.base[k] + p];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                v[j][k] = t[j];
+                par[j] ^= bitsT[(size_t)bit * VEC + j]; // warp-uniform
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+            if (first)
+            {
+                synw[j] = par[j];
+                if (lane == 0)
+                    synT[(size_t)p * VEC + j] = par[j];
+            }
+            else
+                bad[j] |= ((par[j] ^ synw[j]) >> lane) & 1u; // parity of the decisions != target: this frame's check is unsatisfied
+            const bool syn = ((synw[j] >> lane) & 1u) != 0;
+            Math::template check_fast<W>(v[j], syn, thr_eff, want_inf);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+        {
+            double t[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                t[j] = v[j][k];
+            VecIO<double, VEC>::store(row[k], t);
         }
     }
 

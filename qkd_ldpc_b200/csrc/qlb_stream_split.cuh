@@ -80,26 +80,29 @@ namespace qlb
         c.total = o;
         return c;
     }
-    __host__ __device__ inline size_t split_bundle_bytes(int n, int m, int slots, int vec, int bundle)
+    // real_bytes: 4 (fp32 messages) or 8 (fp64)
+    __host__ __device__ inline size_t split_bundle_bytes(int n, int m, int slots, int vec, int bundle, int real_bytes)
     {
-        return align_up((size_t)slots * bundle * 32 * vec * 4, 256) + (size_t)bundle * split_small_carve(n, m, vec).total;
+        return align_up((size_t)slots * bundle * 32 * vec * real_bytes, 256) + (size_t)bundle * split_small_carve(n, m, vec).total;
     }
 
+    template <typename Real>
     struct SplitGroup
     {
-        float *msg;        // row of slot s for this group: msg + s * row_stride (+ VEC * lane)
-        size_t row_stride; // B * G floats
+        Real *msg;         // row of slot s for this group: msg + s * row_stride (+ VEC * lane)
+        size_t row_stride; // B * G values
         uint32_t *bobT, *aliceT, *zT, *synT;
     };
-    __device__ __forceinline__ SplitGroup split_group(const SplitState &st, const CodeDev &code, int vec, uint32_t g)
+    template <typename Real>
+    __device__ __forceinline__ SplitGroup<Real> split_group(const SplitState &st, const CodeDev &code, int vec, uint32_t g)
     {
         const int B = st.bundle, G = 32 * vec;
         const uint32_t bu = g / (uint32_t)B, gb = g % (uint32_t)B;
         const SplitSmall cv = split_small_carve(code.n, code.m, vec);
         unsigned char *p = st.bundles + (size_t)bu * st.bundle_stride;
-        unsigned char *small = p + align_up((size_t)code.slots * B * G * 4, 256) + (size_t)gb * cv.total;
-        SplitGroup r;
-        r.msg = reinterpret_cast<float *>(p) + (size_t)gb * G;
+        unsigned char *small = p + align_up((size_t)code.slots * B * G * sizeof(Real), 256) + (size_t)gb * cv.total;
+        SplitGroup<Real> r;
+        r.msg = reinterpret_cast<Real *>(p) + (size_t)gb * G;
         r.row_stride = (size_t)B * G;
         r.bobT = reinterpret_cast<uint32_t *>(small + cv.bobT);
         r.aliceT = reinterpret_cast<uint32_t *>(small + cv.aliceT);
@@ -127,7 +130,7 @@ namespace qlb
     }
 
     // ---- set-up, part 1: transposed keys / syndromes and frame bookkeeping; one CTA per group at a time --------------------------
-    template <bool kReconcile, int VEC>
+    template <typename Real, bool kReconcile, int VEC>
     __global__ void __launch_bounds__(kSplitSetupThreads) stream_setup_kernel(const DecodeArgs args, const SplitState st)
     {
         constexpr int G = 32 * VEC;
@@ -135,7 +138,7 @@ namespace qlb
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         for (uint32_t g = blockIdx.x; g < (uint32_t)st.n_groups; g += gridDim.x)
         {
-            const SplitGroup sg = split_group(st, code, VEC, g);
+            const SplitGroup<Real> sg = split_group<Real>(st, code, VEC, g);
             const long long f0 = (st.group0 + g) * G;
             if (kReconcile)
             {
@@ -181,14 +184,27 @@ namespace qlb
     // ---- set-up, part 2: messages <- priors (src/qkd_ldpc_algorithm.cpp:182-190), Alice's bit riding in bit 0 (reconcile mode) so
     // that the first check pass yields her syndrome; decisions <- 0. Same work split as the bit pass: (bundle, chunk of bits),
     // adjacent warps on the B groups of the bundle, so the scattered rows are written in 2 KB units.
-    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    template <typename P, typename Real>
+    __device__ __forceinline__ Real stream_unit()
+    {
+        if constexpr (P::kLsbDecision)
+            return P::Rule::kUnit;
+        else
+            return Real(1);
+    }
+    // the prior of a bit whose received value is `bb` (src/qkd_ldpc_algorithm.cpp:401-405): +-lp
+    __device__ __forceinline__ float stream_signed(float lp, uint32_t bb) { return __uint_as_float(__float_as_uint(lp) ^ (bb << 31)); }
+    __device__ __forceinline__ double stream_signed(double lp, uint32_t bb) { return __hiloint2double(__double2hiint(lp) ^ (int)(bb << 31), __double2loint(lp)); }
+
+    template <typename P, bool kReconcile, int kBW, int VEC>
     __global__ void __launch_bounds__(kSplitBitThreads) stream_init_kernel(const DecodeArgs args, const SplitState st)
     {
+        typedef typename P::real Real;
         constexpr int G = 32 * VEC;
         constexpr int kWarps = kSplitBitThreads / 32;
         const CodeDev &code = args.code;
         const int n = code.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const float unit = Rule::kUnit;
+        const Real unit = stream_unit<P, Real>();
         const int B = st.bundle, step = kWarps / B;
         const uint32_t n_bundles = (uint32_t)((st.n_groups + B - 1) / B);
         const uint32_t chunks = ((uint32_t)n + kSplitBitChunk - 1) / kSplitBitChunk;
@@ -199,39 +215,45 @@ namespace qlb
             const int i0 = (int)(item % chunks) * kSplitBitChunk, i1 = min(n, i0 + kSplitBitChunk);
             if (g >= (uint32_t)st.n_groups)
                 continue;
-            const SplitGroup sg = split_group(st, code, VEC, g);
+            const SplitGroup<Real> sg = split_group<Real>(st, code, VEC, g);
             const long long f0 = (st.group0 + g) * G;
-            float lp[VEC];
+            Real lp[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
             {
                 const long long f = f0 + (long long)VEC * lane + j;
-                lp[j] = (kReconcile && f < args.n_frames) ? unit * (float)args.log_prior[f] : 0.f;
+                lp[j] = (kReconcile && f < args.n_frames) ? unit * (Real)args.log_prior[f] : Real(0);
             }
             for (int i = i0 + warp / B; i < i1; i += step)
             {
-                float pv[VEC];
+                Real pv[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
                 {
-                    float prior;
+                    Real prior;
                     uint32_t abit = 0;
                     if (kReconcile)
                     {
                         const uint32_t bb = (sg.bobT[(size_t)i * VEC + j] >> lane) & 1u;
                         abit = (sg.aliceT[(size_t)i * VEC + j] >> lane) & 1u;
-                        prior = __uint_as_float(__float_as_uint(lp[j]) ^ (bb << 31));
+                        prior = stream_signed(lp[j], bb);
                     }
                     else
                     {
                         const long long f = f0 + (long long)VEC * lane + j;
-                        prior = f < args.n_frames ? __fmul_rn(unit, (float)args.llr[f * n + i]) : 0.f;
+                        if constexpr (P::kLsbDecision)
+                            prior = f < args.n_frames ? __fmul_rn(unit, (float)args.llr[f * n + i]) : 0.f;
+                        else
+                            prior = f < args.n_frames ? args.llr[f * n + i] : 0.;
                     }
-                    pv[j] = __uint_as_float((__float_as_uint(prior) & ~1u) | abit);
+                    if constexpr (P::kLsbDecision)
+                        pv[j] = __uint_as_float((__float_as_uint(prior) & ~1u) | abit); // Alice's bit rides in bit 0 through the first check pass
+                    else
+                        pv[j] = prior; // unclamped (:182-190)
                 }
 #pragma unroll
                 for (int a = 0; a < kBW; ++a)
-                    VecIO<VEC>::store(sg.msg + ((size_t)code.bit_slots32[(size_t)a * n + i] * sg.row_stride + VEC * lane), pv);
+                    VecIO<Real, VEC>::store(sg.msg + ((size_t)code.bit_slots32[(size_t)a * n + i] * sg.row_stride + VEC * lane), pv);
                 if (lane == 0)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j)
@@ -241,9 +263,10 @@ namespace qlb
     }
 
     // ---- check pass over the live bundles: work item = (bundle, kSplitCheckChunk consecutive sorted checks) -------------------
-    template <typename Rule, bool kReconcile, int VEC>
+    template <typename P, bool kReconcile, int VEC>
     __global__ void __launch_bounds__(kSplitCheckThreads, QLB_SPLIT_CHECK_MINB) stream_check_kernel(const DecodeArgs args, const SplitState st, int it)
     {
+        typedef typename P::real Real;
         constexpr int kWarps = kSplitCheckThreads / 32;
         __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
         const uint32_t n_live = *st.n_live;
@@ -254,7 +277,10 @@ namespace qlb
         if (threadIdx.x == 0)
             split_segments(code, s_seg_w, s_seg_lo, s_seg_hi);
         __syncthreads();
-        const float cap = args.cap_f32 * Rule::kUnit;
+        const float cap = args.cap_f32 * (float)stream_unit<P, Real>();
+        const double thr_eff = args.enable_thr ? args.thr : __longlong_as_double(0x7ff0000000000000LL); // fp64: the clamp as an operand
+        const bool want_inf = !(thr_eff <= 700.);
+        (void)cap; (void)thr_eff; (void)want_inf;
         const bool first = kReconcile && it == 0;
         const uint32_t chunks = ((uint32_t)m + kSplitCheckChunk - 1) / kSplitCheckChunk;
         const unsigned long long items = (unsigned long long)n_live * chunks;
@@ -271,8 +297,10 @@ namespace qlb
                 alive |= st.act[g * 4 + j];
             if (!alive)
                 continue; // every frame of this group has converged: its rows are left alone
-            const SplitGroup sg = split_group(st, code, VEC, g);
-            float *__restrict__ msg = sg.msg;
+            const SplitGroup<Real> sg = split_group<Real>(st, code, VEC, g);
+            Real *__restrict__ msg = sg.msg;
+            const uint32_t *bitsT = first ? sg.aliceT : sg.zT; // fp64: what a check's parity is formed from
+            (void)bitsT;
             const size_t rs = sg.row_stride;
             uint32_t bad[VEC];
 #pragma unroll
@@ -290,7 +318,13 @@ namespace qlb
                             prefetch_l2(msg + ((size_t)(code.base[k] + p + step) * rs + VEC * lane));
                 switch (s_seg_w[s])
                 {
-#define QLB_PSEG(W_) case W_: stream_check<Rule, W_, VEC>(msg, code, p, lane, sg.synT, cap, first, bad, rs); break;
+#define QLB_PSEG(W_)                                                                                                          \
+    case W_:                                                                                                                  \
+        if constexpr (P::kLsbDecision)                                                                                        \
+            stream_check<typename P::Rule, W_, VEC>(msg, code, p, lane, sg.synT, cap, first, bad, rs);                        \
+        else                                                                                                                  \
+            stream_check64<typename P::Math, W_, VEC>(msg, code, p, lane, sg.synT, bitsT, thr_eff, want_inf, first, bad, rs); \
+        break;
                     QLB_PSEG(1) QLB_PSEG(2) QLB_PSEG(3) QLB_PSEG(4) QLB_PSEG(5) QLB_PSEG(6) QLB_PSEG(7) QLB_PSEG(8)
                     QLB_PSEG(9) QLB_PSEG(10) QLB_PSEG(11) QLB_PSEG(12) QLB_PSEG(13) QLB_PSEG(14) QLB_PSEG(15) QLB_PSEG(16)
 #undef QLB_PSEG
@@ -375,14 +409,16 @@ namespace qlb
 
     // ---- bit pass over the live bundles: work item = (bundle, kSplitBitChunk consecutive bits), U bits per warp in flight -----------
     // fr[j]: frame index held by this lane's column j (kNoFrame: none)
-    template <bool kReconcile, int kBW, int VEC, int U>
-    __device__ __forceinline__ void split_bits(const DecodeArgs &args, const SplitGroup &sg, const int (&bit)[U], int lane, const float (&lp)[VEC],
-                                               const uint32_t (&act_word)[VEC], const uint32_t (&fr)[VEC], float unit, float cap, bool clamp_b2c)
+    template <typename P, bool kReconcile, int kBW, int VEC, int U>
+    __device__ __forceinline__ void split_bits(const DecodeArgs &args, const SplitGroup<typename P::real> &sg, const int (&bit)[U], int lane,
+                                               const typename P::real (&lp)[VEC], const uint32_t (&act_word)[VEC], const uint32_t (&fr)[VEC],
+                                               typename P::real unit, typename P::real cap, bool clamp_b2c)
     {
+        typedef typename P::real Real;
         const CodeDev &code = args.code;
         const int n = code.n;
-        float *row[U][kBW];
-        float c[U][kBW][VEC];
+        Real *row[U][kBW];
+        Real c[U][kBW][VEC];
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -392,41 +428,48 @@ namespace qlb
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int a = 0; a < kBW; ++a)
-                VecIO<VEC>::load(row[u][a], c[u][a]);
+                VecIO<Real, VEC>::load(row[u][a], c[u][a]);
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
             const int i = bit[u];
-            float total[VEC];
+            Real total[VEC];
             uint32_t zbits = 0;
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
             {
-                float prior;
+                Real prior;
                 if (kReconcile)
-                    prior = __uint_as_float(__float_as_uint(lp[j]) ^ (((sg.bobT[(size_t)i * VEC + j] >> lane) & 1u) << 31));
-                else
+                    prior = stream_signed(lp[j], (sg.bobT[(size_t)i * VEC + j] >> lane) & 1u);
+                else if constexpr (P::kLsbDecision)
                     prior = fr[j] != kNoFrame ? __fmul_rn(unit, (float)args.llr[(size_t)fr[j] * n + i]) : 0.f;
-                float t = prior;
+                else
+                    prior = fr[j] != kNoFrame ? args.llr[(size_t)fr[j] * n + i] : 0.;
+                Real t = prior; // left to right from the prior, in the bit's arrival order (:256-258)
 #pragma unroll
                 for (int a = 0; a < kBW; ++a)
                     t = t + c[u][a][j];
                 total[j] = t;
-                zbits |= (uint32_t)(t <= 0.f) << j;
+                zbits |= (uint32_t)(t <= Real(0)) << j; // :259-266 (a NaN total decides 0)
             }
 #pragma unroll
             for (int a = 0; a < kBW; ++a)
             {
-                float o[VEC];
+                Real o[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
                 {
-                    float v = total[j] - c[u][a][j];
-                    if (clamp_b2c)
-                        v = fminf(fmaxf(v, -cap), cap);
-                    o[j] = __uint_as_float((__float_as_uint(v) & ~1u) | ((zbits >> j) & 1u));
+                    Real v = total[j] - c[u][a][j]; // :300-311
+                    if constexpr (P::kLsbDecision)
+                    {
+                        if (clamp_b2c)
+                            v = fminf(fmaxf(v, -cap), cap);
+                        o[j] = __uint_as_float((__float_as_uint(v) & ~1u) | ((zbits >> j) & 1u));
+                    }
+                    else
+                        o[j] = clamp_f64(v, cap); // :313-316; cap = +inf when the clamp is disabled, NaN passes
                 }
-                VecIO<VEC>::store(row[u][a], o);
+                VecIO<Real, VEC>::store(row[u][a], o);
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
@@ -441,9 +484,10 @@ namespace qlb
         }
     }
 
-    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    template <typename P, bool kReconcile, int kBW, int VEC>
     __global__ void __launch_bounds__(kSplitBitThreads, QLB_SPLIT_BIT_MINB) stream_bit_kernel(const DecodeArgs args, const SplitState st)
     {
+        typedef typename P::real Real;
         constexpr int G = 32 * VEC;
         constexpr int kWarps = kSplitBitThreads / 32;
         const uint32_t n_live = *st.n_live;
@@ -451,9 +495,16 @@ namespace qlb
             return;
         const CodeDev &code = args.code;
         const int n = code.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const float unit = Rule::kUnit;
-        const float cap = args.cap_f32 * unit;
-        const bool clamp_b2c = !(Rule::kUnit != 1.f && cap >= 25.f);
+        const Real unit = stream_unit<P, Real>();
+        Real cap;
+        bool clamp_b2c = true;
+        if constexpr (P::kLsbDecision)
+        {
+            cap = args.cap_f32 * unit;
+            clamp_b2c = !(unit != 1.f && cap >= 25.f);
+        }
+        else
+            cap = args.enable_thr ? args.thr : __longlong_as_double(0x7ff0000000000000LL);
         const uint32_t chunks = ((uint32_t)n + kSplitBitChunk - 1) / kSplitBitChunk;
         const unsigned long long items = (unsigned long long)n_live * chunks;
         const int B = st.bundle, step = kWarps / B; // adjacent warps: the B groups of the bundle on the same bit
@@ -463,14 +514,14 @@ namespace qlb
             const int i0 = (int)(item % chunks) * kSplitBitChunk, i1 = min(n, i0 + kSplitBitChunk);
             if (g >= (uint32_t)st.n_groups)
                 continue;
-            const SplitGroup sg = split_group(st, code, VEC, g);
-            float lp[VEC];
+            const SplitGroup<Real> sg = split_group<Real>(st, code, VEC, g);
+            Real lp[VEC];
             uint32_t act_word[VEC], fr[VEC], alive = 0;
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
             {
                 fr[j] = st.fmap[(size_t)g * G + VEC * lane + j];
-                lp[j] = (kReconcile && fr[j] != kNoFrame) ? unit * (float)args.log_prior[fr[j]] : 0.f;
+                lp[j] = (kReconcile && fr[j] != kNoFrame) ? unit * (Real)args.log_prior[fr[j]] : Real(0);
                 act_word[j] = st.act[g * 4 + j];
                 alive |= act_word[j];
             }
@@ -485,13 +536,13 @@ namespace qlb
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     many[u] = i + u * step;
-                split_bits<kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, fr, unit, cap, clamp_b2c);
+                split_bits<P, kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, fr, unit, cap, clamp_b2c);
             }
 #pragma unroll 1
             for (; i < i1; i += step)
             {
                 const int one[1] = {i};
-                split_bits<kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, fr, unit, cap, clamp_b2c);
+                split_bits<P, kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, fr, unit, cap, clamp_b2c);
             }
         }
     }
@@ -499,7 +550,7 @@ namespace qlb
     // ---- results: flags, key comparison, decoded keys and syndromes back in frame-major order; one CTA per group at a time ----
     // only_done: called from a repack (and only when one was decided): the frames that have finished -- about to lose their
     // columns -- get their results now; the final call handles whatever the map still holds.
-    template <bool kReconcile, int VEC>
+    template <typename Real, bool kReconcile, int VEC>
     __global__ void __launch_bounds__(kSplitSetupThreads) stream_finalize_kernel(const DecodeArgs args, const SplitState st, int only_done)
     {
         constexpr int G = 32 * VEC;
@@ -511,7 +562,7 @@ namespace qlb
         const int n = code.n, m = code.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         for (uint32_t g = blockIdx.x; g < (uint32_t)st.n_groups; g += gridDim.x)
         {
-            const SplitGroup sg = split_group(st, code, VEC, g);
+            const SplitGroup<Real> sg = split_group<Real>(st, code, VEC, g);
             const uint32_t *fmap_g = st.fmap + (size_t)g * G;
             uint32_t keep[VEC], fr[VEC], any = 0; // keep[j] bit l: column (l, j) holds a frame this call reports
 #pragma unroll
@@ -668,21 +719,21 @@ namespace qlb
     // message columns: one CTA owns a slot at a time (all groups of the wave), staging <= kRepackStage values between the reads
     // and the writes
     constexpr int kRepackStage = 4096, kRepackThreads = 256;
-    template <int VEC>
+    template <typename Real, int VEC>
     __global__ void __launch_bounds__(kRepackThreads) stream_repack_msg_kernel(const DecodeArgs args, const SplitState st)
     {
         constexpr int G = 32 * VEC;
-        __shared__ float s_val[kRepackStage];
+        __shared__ Real s_val[kRepackStage];
         if (!st.repack[0])
             return;
         const uint32_t live = st.repack[1];
         const int B = st.bundle;
         const size_t rs = (size_t)B * G;
         const int slots = args.code.slots;
-        auto at = [&](uint32_t slot, uint32_t col_id) -> float *
+        auto at = [&](uint32_t slot, uint32_t col_id) -> Real *
         {
             const uint32_t g = col_id / G, c = col_id % G;
-            return reinterpret_cast<float *>(st.bundles + (size_t)(g / B) * st.bundle_stride) + ((size_t)slot * rs + (size_t)(g % B) * G + c);
+            return reinterpret_cast<Real *>(st.bundles + (size_t)(g / B) * st.bundle_stride) + ((size_t)slot * rs + (size_t)(g % B) * G + c);
         };
         for (uint32_t slot = blockIdx.x; slot < (uint32_t)slots; slot += gridDim.x)
             for (uint32_t k0 = 0; k0 < live; k0 += kRepackStage)
@@ -698,7 +749,7 @@ namespace qlb
     }
 
     // bit-transposed words (Bob, Alice, decisions: per bit; syndromes: per check): one warp owns a node of one array at a time
-    template <int VEC>
+    template <typename Real, int VEC>
     __global__ void __launch_bounds__(kRepackThreads) stream_repack_bits_kernel(const DecodeArgs args, const SplitState st)
     {
         constexpr int G = 32 * VEC;
@@ -711,7 +762,7 @@ namespace qlb
         const uint32_t new_groups = st.repack[2];
         const SplitSmall cv = split_small_carve(n, m, VEC);
         const int B = st.bundle;
-        const size_t small0 = align_up((size_t)code.slots * B * G * 4, 256);
+        const size_t small0 = align_up((size_t)code.slots * B * G * sizeof(Real), 256);
         const unsigned long long nodes = 3ull * n + m;
         for (unsigned long long q = (unsigned long long)blockIdx.x * kWarps + warp; q < nodes; q += (unsigned long long)gridDim.x * kWarps)
         {

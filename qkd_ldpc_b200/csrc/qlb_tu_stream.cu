@@ -7,15 +7,16 @@ namespace
 {
     // The streaming decoder (qlb_stream_split.cuh): one kernel per pass over all groups, in waves when device memory cannot
     // hold the message arrays of every group at once. Nothing here waits for the device.
-    template <typename Rule, bool kReconcile, int kBW, int VEC>
+    template <typename P, bool kReconcile, int kBW, int VEC>
     int launch_stream_split(qlb_ctx *ctx, DecodeArgs &args, size_t budget)
     {
+        typedef typename P::real Real;
         const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
         // groups per bundle: 2 KB of contiguous memory per slot when there are enough groups (see qlb_stream_split.cuh)
-        int B = VEC == 4 ? 4 : 1; // measured on B200, N = 100 000: B = 1 / 2 / 4 / 8 -> 0.589 / 0.668 / 0.789 / 0.783 of the copy bandwidth
+        int B = VEC == P::kVecWide ? 4 : 1; // measured on B200, N = 100 000, fp32: B = 1 / 2 / 4 / 8 -> 0.589 / 0.668 / 0.789 / 0.783 of the copy bandwidth
         while (B > 1 && groups < B)
             B /= 2;
-        const size_t per_bundle = split_bundle_bytes(args.code.n, args.code.m, args.code.slots, VEC, B);
+        const size_t per_bundle = split_bundle_bytes(args.code.n, args.code.m, args.code.slots, VEC, B, (int)sizeof(Real));
         long long fit_bundles = (long long)(budget / per_bundle);
         if (args.stream_max_bundles > 0) // qlb_decode_params.stream_max_bundles: waves without filling the device memory
             fit_bundles = std::min<long long>(fit_bundles, args.stream_max_bundles);
@@ -49,15 +50,15 @@ namespace
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;
 
-        auto k_setup = stream_setup_kernel<kReconcile, VEC>;
-        auto k_init = stream_init_kernel<Rule, kReconcile, kBW, VEC>;
-        auto k_check = stream_check_kernel<Rule, kReconcile, VEC>;
+        auto k_setup = stream_setup_kernel<Real, kReconcile, VEC>;
+        auto k_init = stream_init_kernel<P, kReconcile, kBW, VEC>;
+        auto k_check = stream_check_kernel<P, kReconcile, VEC>;
         auto k_update = stream_update_kernel<VEC>;
-        auto k_bit = stream_bit_kernel<Rule, kReconcile, kBW, VEC>;
-        auto k_final = stream_finalize_kernel<kReconcile, VEC>;
+        auto k_bit = stream_bit_kernel<P, kReconcile, kBW, VEC>;
+        auto k_final = stream_finalize_kernel<Real, kReconcile, VEC>;
         auto k_plan = stream_repack_plan_kernel<VEC>;
-        auto k_mvmsg = stream_repack_msg_kernel<VEC>;
-        auto k_mvbits = stream_repack_bits_kernel<VEC>;
+        auto k_mvmsg = stream_repack_msg_kernel<Real, VEC>;
+        auto k_mvbits = stream_repack_bits_kernel<Real, VEC>;
         auto k_commit = stream_repack_commit_kernel<VEC>;
         // rounds after which a repack is attempted (decided on the device: live columns <= half of the streamed ones)
         const bool repack_on = !args.stream_no_repack && per_wave <= kMaxRepackGroups && per_wave >= 2;
@@ -105,29 +106,47 @@ namespace
         return QLB_OK;
     }
 
-    template <typename Rule, bool kReconcile>
-    int launch_stream_bw(qlb_ctx *ctx, DecodeArgs &args)
+    template <typename P, bool kReconcile, int kBW>
+    int launch_stream_vec(qlb_ctx *ctx, DecodeArgs &args)
     {
         size_t free_b = 0, total_b = 0;
         QLB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t budget = (free_b + ctx->scratch.cap) / 20 * 17;
-        // 128-frame groups (128-bit accesses); a batch of <= 32 frames takes 32-frame groups
-        return args.n_frames > 32 ? launch_stream_split<Rule, kReconcile, 3, 4>(ctx, args, budget) : launch_stream_split<Rule, kReconcile, 3, 1>(ctx, args, budget);
+        // groups of 128 (fp32) / 64 (fp64) frames: 128-bit accesses; a batch of <= 32 frames takes 32-frame groups
+        return args.n_frames > 32 ? launch_stream_split<P, kReconcile, kBW, P::kVecWide>(ctx, args, budget) : launch_stream_split<P, kReconcile, kBW, 1>(ctx, args, budget);
     }
 
-    bool stream_eligible_impl(const CodeDev &c)
+    template <typename P, bool kReconcile>
+    int launch_stream_bw(qlb_ctx *ctx, DecodeArgs &args)
     {
-        // column weight 3 (the code family of BASELINE.json) only: other weights take the generic kernel
-        return c.uniform_bit_w == 3 && c.max_check_w <= kResidentMaxCW && c.m <= c.n;
+        switch (args.code.uniform_bit_w)
+        {
+#ifndef QLB_STREAM_LEAN // kernel-tuning builds (scripts/build_stream_variants.py) compile the bit weight of the benchmark codes only
+        case 2: return launch_stream_vec<P, kReconcile, 2>(ctx, args);
+        case 4: return launch_stream_vec<P, kReconcile, 4>(ctx, args);
+#endif
+        case 3: return launch_stream_vec<P, kReconcile, 3>(ctx, args);
+        default: return fail(QLB_ERR_UNSUPPORTED, "streaming decoder: unsupported bit weight");
+        }
     }
 }
 namespace qlb
 {
-    bool stream_f32_eligible(const CodeDev &c) { return stream_eligible_impl(c); }
+    // uniform column weight 2, 3 or 4 (BASELINE.json's code family is CW = 3); irregular bit weights take the generic kernel
+    bool stream_eligible(const CodeDev &c)
+    {
+        return c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW && c.m <= c.n && c.col_of_slot32 != nullptr;
+    }
     int launch_stream_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast)
     {
         if (fast)
-            return reconcile ? launch_stream_bw<RuleF32Fast, true>(ctx, args) : launch_stream_bw<RuleF32Fast, false>(ctx, args);
-        return reconcile ? launch_stream_bw<RuleF32Accurate, true>(ctx, args) : launch_stream_bw<RuleF32Accurate, false>(ctx, args);
+            return reconcile ? launch_stream_bw<StreamF32<RuleF32Fast>, true>(ctx, args) : launch_stream_bw<StreamF32<RuleF32Fast>, false>(ctx, args);
+        return reconcile ? launch_stream_bw<StreamF32<RuleF32Accurate>, true>(ctx, args) : launch_stream_bw<StreamF32<RuleF32Accurate>, false>(ctx, args);
+    }
+    int launch_stream_f64(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fused)
+    {
+        if (fused)
+            return reconcile ? launch_stream_bw<StreamF64<MathF64Fused>, true>(ctx, args) : launch_stream_bw<StreamF64<MathF64Fused>, false>(ctx, args);
+        return reconcile ? launch_stream_bw<StreamF64<MathF64>, true>(ctx, args) : launch_stream_bw<StreamF64<MathF64>, false>(ctx, args);
     }
 }

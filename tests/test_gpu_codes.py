@@ -195,3 +195,69 @@ def test_block_length_one_million(ctx, oracle):
                 ok = want[:, 1] == 1
                 assert (capi.unpack_bits(dec, n)[ok] == wdec[ok]).all()
                 assert (np.abs(it.astype(int) - want[:, 0].astype(int)) <= 1).all()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_streaming_fp64_equals_resident_kernel(ctx, oracle, fused):
+    """The fp64 streaming decoder (64-frame groups, the reference's check rule, parity from the packed decisions) forced with the
+    tier-3 hook on the N=10240 code: iterations, flags, every decoded bit (failed frames included) and syndromes must equal the
+    fp64 SM-resident kernel's -- which equals the reference on the campaign -- for 700 mixed-QBER frames (11 groups = 3 bundles,
+    the last ragged; several repacks), without repacks, in waves, for a <= 32-frame batch, with the clamp off (NaN semantics)
+    and through the sum-product entry."""
+    mat = codes.load_npz(codes.NORTH_STAR)
+    code = capi.Code.from_graph(mat)
+    A, B, Q = [], [], []
+    for pt, (q, cnt) in enumerate(((0.03, 200), (0.06, 150), (0.08, 150), (0.085, 120), (0.0875, 50), (0.09, 30))):
+        a, b, ex = ctx.generate(mat.n, oracle.trial_seeds(5150 + pt, cnt), q)
+        A.append(a); B.append(b); Q.append(np.full(cnt, ex))
+    A, B, Q = np.concatenate(A), np.concatenate(B), np.concatenate(Q)
+    perm = np.random.default_rng(3).permutation(len(Q))
+    A, B, Q = np.ascontiguousarray(A[perm]), np.ascontiguousarray(B[perm]), Q[perm]
+    r = ctx.reconcile_packed(code, capi.make_params(64, 100, 100.0, True, fast_math=fused), A, B, Q, want_decoded=True, want_syndrome=True)
+    assert 0 < int((r[1] & 1).sum()) < len(Q)
+    for kw in ({}, {"stream_no_repack": True}, {"stream_max_bundles": 1}):
+        s = ctx.reconcile_packed(code, capi.make_params(64, 100, 100.0, True, fast_math=fused, tier=3, **kw), A, B, Q, want_decoded=True, want_syndrome=True)
+        assert (r[0] == s[0]).all(), (kw, np.flatnonzero(r[0] != s[0])[:10])
+        assert all((x == y).all() for x, y in zip(r[1:], s[1:])), kw
+    # <= 32 frames: the 32-frame-group instantiation; and the clamp off (saturated products -> inf -> NaN totals, :508-524)
+    for thr_on in (True, False):
+        r21 = ctx.reconcile_packed(code, capi.make_params(64, 40, 100.0, thr_on, fast_math=fused), A[:21], B[:21], Q[:21], want_decoded=True, want_syndrome=True)
+        s21 = ctx.reconcile_packed(code, capi.make_params(64, 40, 100.0, thr_on, fast_math=fused, tier=3), A[:21], B[:21], Q[:21], want_decoded=True, want_syndrome=True)
+        assert all((x == y).all() for x, y in zip(r21, s21)), thr_on
+    r100 = ctx.reconcile_packed(code, capi.make_params(64, 40, 100.0, False, fast_math=fused), A[:100], B[:100], Q[:100], want_decoded=True)
+    s100 = ctx.reconcile_packed(code, capi.make_params(64, 40, 100.0, False, fast_math=fused, tier=3), A[:100], B[:100], Q[:100], want_decoded=True)
+    assert all((x == y).all() for x, y in zip(r100[:3], s100[:3]))
+    # the sum-product entry: arbitrary LLRs + target syndromes
+    k = 90
+    bob = capi.unpack_bits(B[:k], mat.n)
+    rng = np.random.default_rng(17)
+    llr = np.where(bob != 0, -1.0, 1.0) * np.log((1 - Q[:k]) / Q[:k])[:, None] * rng.uniform(0.6, 1.4, size=bob.shape)
+    syn = capi.unpack_bits(r[3][:k], mat.m)
+    it_r, res_r, bits_r = ctx.sum_product(code, capi.make_params(64, 60, 100.0, True, fast_math=fused), llr, syn)
+    it_s, res_s, bits_s = ctx.sum_product(code, capi.make_params(64, 60, 100.0, True, fast_math=fused, tier=3), llr, syn)
+    assert (it_r == it_s).all() and (res_r == res_s).all() and (bits_r == bits_s).all()
+
+
+@pytest.mark.parametrize("dv", [2, 4])
+def test_streaming_other_bit_weights(ctx, oracle, dv):
+    """Column weights 2 and 4 through the streaming decoder (template instantiations of the bit pass) on a permutation code of
+    N = 4 096: fp64 must equal the oracle on iterations, flags and decoded bits; fp32 must equal the generic fp32 kernel's flags."""
+    n, m = 4096, 2048
+    mat = codes.permutation_code(n, m, dv, 4321)
+    g, code = graph_of(mat), capi.Code.from_graph(mat)
+    for q in ((0.01, 0.02) if dv == 2 else (0.04, 0.09)):
+        seeds = oracle.trial_seeds(2024 + dv, 150)
+        want, wdec = oracle.run_trials(g, q, seeds, threads=8, max_it=30, want_decoded=True)
+        a, b, ex = ctx.generate(n, seeds, q)
+        Q = np.full(len(seeds), ex)
+        for fused in (False, True):
+            it, res, dec, syn = ctx.reconcile_packed(code, capi.make_params(64, 30, 100.0, True, fast_math=fused, tier=3), a, b, Q, want_decoded=True,
+                                                     want_syndrome=True)
+            assert ((res & 1) == want[:, 1]).all() and (((res >> 1) & 1) == want[:, 2]).all(), (dv, q, fused)
+            assert (it == want[:, 0]).all(), (dv, q, fused, np.flatnonzero(it != want[:, 0])[:8])
+            assert (capi.unpack_bits(dec, n) == wdec).all()
+        for fast in (False, True):
+            gen = ctx.reconcile_packed(code, capi.make_params(32, 30, 100.0, True, fast_math=fast, tier=2), a, b, Q)
+            st = ctx.reconcile_packed(code, capi.make_params(32, 30, 100.0, True, fast_math=fast, tier=3), a, b, Q)
+            assert ((gen[1] & 3) == (st[1] & 3)).mean() >= 0.98, (dv, q, fast)
+            assert (np.abs(gen[0].astype(int) - st[0].astype(int)) <= 1).mean() >= 0.95
