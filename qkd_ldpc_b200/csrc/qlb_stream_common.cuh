@@ -109,14 +109,14 @@ namespace qlb
     // row_stride: floats between the rows of consecutive slots (G, or B * G when B groups are interleaved slot by slot)
     template <typename Rule, int W, int VEC>
     __device__ __forceinline__ void stream_check(float *__restrict__ msg, const CodeDev &code, uint32_t p, int lane, uint32_t *__restrict__ synT,
-                                                 float cap, bool first, uint32_t (&bad)[VEC], size_t row_stride = 32 * VEC)
+                                                 float cap, bool first, uint32_t (&bad)[VEC], uint32_t row_stride)
     {
         float v[VEC][W];
         float *row[W];
 #pragma unroll
         for (int k = 0; k < W; ++k)
         {
-            row[k] = msg + ((size_t)(code.base[k] + p) * row_stride + VEC * lane);
+            row[k] = msg + VEC * lane + (size_t)((code.base[k] + p) * row_stride); // 32-bit product (slots * row_stride < 2^32)
             float t[VEC];
             VecIO<float, VEC>::load(row[k], t);
 #pragma unroll
@@ -167,7 +167,7 @@ namespace qlb
     template <typename Math, int W, int VEC>
     __device__ __forceinline__ void stream_check64(double *__restrict__ msg, const CodeDev &code, uint32_t p, int lane, uint32_t *__restrict__ synT,
                                                    const uint32_t *__restrict__ bitsT, double thr_eff, bool want_inf, bool first, uint32_t (&bad)[VEC],
-                                                   size_t row_stride)
+                                                   uint32_t row_stride)
     {
         double v[VEC][W];
         double *row[W];
@@ -181,7 +181,7 @@ namespace qlb
 #pragma unroll
         for (int k = 0; k < W; ++k)
         {
-            row[k] = msg + ((size_t)(code.base[k] + p) * row_stride + VEC * lane);
+            row[k] = msg + VEC * lane + (size_t)((code.base[k] + p) * row_stride); // 32-bit product (slots * row_stride < 2^32)
             double t[VEC];
             VecIO<double, VEC>::load(row[k], t);
             const uint32_t bit = code.col_of_slot32[code.base[k] + p];

@@ -38,8 +38,21 @@ namespace qlb
 #ifndef QLB_SPLIT_BIT_U
 #define QLB_SPLIT_BIT_U 2 // bits per warp in flight
 #endif
-    constexpr int kSplitCheckThreads = QLB_SPLIT_CHECK_THREADS, kSplitBitThreads = QLB_SPLIT_BIT_THREADS, kSplitSetupThreads = 512;
-    constexpr int kSplitCheckChunk = 8 * (kSplitCheckThreads / 32); // sorted check positions per work item
+    // the fp64 check pass is bound by FP64 issue, not by the loads in flight: more, leaner warps (measured on B200, below)
+#ifndef QLB_SPLIT64_CHECK_THREADS
+#define QLB_SPLIT64_CHECK_THREADS 256
+#endif
+#ifndef QLB_SPLIT64_CHECK_MINB
+#define QLB_SPLIT64_CHECK_MINB 2
+#endif
+    constexpr int kSplitBitThreads = QLB_SPLIT_BIT_THREADS, kSplitSetupThreads = 512;
+    template <typename P>
+    struct SplitTune
+    {
+        static constexpr int kCheckThreads = P::kLsbDecision ? QLB_SPLIT_CHECK_THREADS : QLB_SPLIT64_CHECK_THREADS;
+        static constexpr int kCheckMinB = P::kLsbDecision ? QLB_SPLIT_CHECK_MINB : QLB_SPLIT64_CHECK_MINB;
+        static constexpr int kCheckChunk = 8 * (kCheckThreads / 32); // sorted check positions per work item
+    };
     constexpr int kSplitBitChunk = 16 * (kSplitBitThreads / 32);    // bits per work item
 
     struct SplitState
@@ -90,7 +103,7 @@ namespace qlb
     struct SplitGroup
     {
         Real *msg;         // row of slot s for this group: msg + s * row_stride (+ VEC * lane)
-        size_t row_stride; // B * G values
+        uint32_t row_stride; // B * G values; slot * row_stride < 2^32 (checked by the launcher), so row offsets are 32-bit products
         uint32_t *bobT, *aliceT, *zT, *synT;
     };
     template <typename Real>
@@ -103,7 +116,7 @@ namespace qlb
         unsigned char *small = p + align_up((size_t)code.slots * B * G * sizeof(Real), 256) + (size_t)gb * cv.total;
         SplitGroup<Real> r;
         r.msg = reinterpret_cast<Real *>(p) + (size_t)gb * G;
-        r.row_stride = (size_t)B * G;
+        r.row_stride = (uint32_t)(B * G);
         r.bobT = reinterpret_cast<uint32_t *>(small + cv.bobT);
         r.aliceT = reinterpret_cast<uint32_t *>(small + cv.aliceT);
         r.zT = reinterpret_cast<uint32_t *>(small + cv.zT);
@@ -253,7 +266,7 @@ namespace qlb
                 }
 #pragma unroll
                 for (int a = 0; a < kBW; ++a)
-                    VecIO<Real, VEC>::store(sg.msg + ((size_t)code.bit_slots32[(size_t)a * n + i] * sg.row_stride + VEC * lane), pv);
+                    VecIO<Real, VEC>::store(sg.msg + VEC * lane + (size_t)(code.bit_slots32[(size_t)a * n + i] * sg.row_stride), pv);
                 if (lane == 0)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j)
@@ -264,9 +277,10 @@ namespace qlb
 
     // ---- check pass over the live bundles: work item = (bundle, kSplitCheckChunk consecutive sorted checks) -------------------
     template <typename P, bool kReconcile, int VEC>
-    __global__ void __launch_bounds__(kSplitCheckThreads, QLB_SPLIT_CHECK_MINB) stream_check_kernel(const DecodeArgs args, const SplitState st, int it)
+    __global__ void __launch_bounds__(SplitTune<P>::kCheckThreads, SplitTune<P>::kCheckMinB) stream_check_kernel(const DecodeArgs args, const SplitState st, int it)
     {
         typedef typename P::real Real;
+        constexpr int kSplitCheckThreads = SplitTune<P>::kCheckThreads, kSplitCheckChunk = SplitTune<P>::kCheckChunk;
         constexpr int kWarps = kSplitCheckThreads / 32;
         __shared__ uint32_t s_seg_w[kResidentMaxCW + 1], s_seg_lo[kResidentMaxCW + 1], s_seg_hi[kResidentMaxCW + 1];
         const uint32_t n_live = *st.n_live;
@@ -301,7 +315,7 @@ namespace qlb
             Real *__restrict__ msg = sg.msg;
             const uint32_t *bitsT = first ? sg.aliceT : sg.zT; // fp64: what a check's parity is formed from
             (void)bitsT;
-            const size_t rs = sg.row_stride;
+            const uint32_t rs = sg.row_stride;
             uint32_t bad[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
@@ -315,7 +329,7 @@ namespace qlb
                 if (p + step < p1) // the rows of this warp's next check -> L2 while this one is computed (cnt[k]: checks with an edge position k)
                     for (int k = 0; k < (int)s_seg_w[s]; ++k)
                         if (p + step < code.cnt[k])
-                            prefetch_l2(msg + ((size_t)(code.base[k] + p + step) * rs + VEC * lane));
+                            prefetch_l2(msg + VEC * lane + (size_t)((code.base[k] + p + step) * rs));
                 switch (s_seg_w[s])
                 {
 #define QLB_PSEG(W_)                                                                                                          \
@@ -423,7 +437,7 @@ namespace qlb
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int a = 0; a < kBW; ++a)
-                row[u][a] = sg.msg + ((size_t)code.bit_slots32[(size_t)a * n + bit[u]] * sg.row_stride + VEC * lane);
+                row[u][a] = sg.msg + VEC * lane + (size_t)(code.bit_slots32[(size_t)a * n + bit[u]] * sg.row_stride);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll

@@ -14,8 +14,10 @@ namespace
         const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
         // groups per bundle: 2 KB of contiguous memory per slot when there are enough groups (see qlb_stream_split.cuh)
         int B = VEC == P::kVecWide ? 4 : 1; // measured on B200, N = 100 000, fp32: B = 1 / 2 / 4 / 8 -> 0.589 / 0.668 / 0.789 / 0.783 of the copy bandwidth
-        while (B > 1 && groups < B)
+        while (B > 1 && (groups < B || (unsigned long long)args.code.slots * B * G >= 0xFFFFFFFFull)) // row offsets are 32-bit
             B /= 2;
+        if ((unsigned long long)args.code.slots * B * G >= 0xFFFFFFFFull)
+            return fail(QLB_ERR_UNSUPPORTED, "streaming decoder: more than 2^32 message values per frame group");
         const size_t per_bundle = split_bundle_bytes(args.code.n, args.code.m, args.code.slots, VEC, B, (int)sizeof(Real));
         long long fit_bundles = (long long)(budget / per_bundle);
         if (args.stream_max_bundles > 0) // qlb_decode_params.stream_max_bundles: waves without filling the device memory
@@ -65,6 +67,7 @@ namespace
         // attempts every 2 / 3 / 4 rounds measured 0.681 / 0.680 / 0.681 at the waterfall, but every second round costs the
         // early-converging QBERs 10 %; a declined attempt costs ~15 us
         auto repack_round = [](int it) { return it >= 4 && it % 4 == 2; };
+        constexpr int kSplitCheckThreads = SplitTune<P>::kCheckThreads;
         int occ_check = 1, occ_bit = 1;
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_check, k_check, kSplitCheckThreads, 0));
         QLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bit, k_bit, kSplitBitThreads, 0));
