@@ -40,23 +40,31 @@ namespace qkd_b200
             throw std::runtime_error(std::string(what) + ": " + qlb_last_error());
     }
 
+    // prefix sums of the node weights; `contiguous`: every row starts where the previous one ends (a matrix loaded by
+    // read_sparse_alist_matrix / read_dense_matrix: its rows are slices of one flat array, matrix_io.cpp)
+    static bool offsets_of(int *const *rows, const int *weights, size_t count, std::vector<int32_t> &ptr)
+    {
+        ptr.assign(count + 1, 0);
+        bool contiguous = true;
+        for (size_t i = 0; i < count; ++i)
+        {
+            ptr[i + 1] = ptr[i] + weights[i];
+            contiguous &= rows[i] == rows[0] + ptr[i];
+        }
+        return contiguous;
+    }
+
     flat_matrix flatten(const H_matrix &h)
     {
         flat_matrix f;
         f.n = static_cast<int32_t>(h.num_bit_nodes);
         f.m = static_cast<int32_t>(h.num_check_nodes);
-        f.row_ptr.assign(1, 0);
-        for (size_t j = 0; j < h.num_check_nodes; ++j)
-        {
-            f.col_idx.insert(f.col_idx.end(), h.check_nodes[j], h.check_nodes[j] + h.check_nodes_weight[j]);
-            f.row_ptr.push_back(static_cast<int32_t>(f.col_idx.size()));
-        }
-        f.col_ptr.assign(1, 0);
-        for (size_t i = 0; i < h.num_bit_nodes; ++i)
-        {
-            f.row_idx.insert(f.row_idx.end(), h.bit_nodes[i], h.bit_nodes[i] + h.bit_nodes_weight[i]);
-            f.col_ptr.push_back(static_cast<int32_t>(f.row_idx.size()));
-        }
+        if (!offsets_of(h.check_nodes, h.check_nodes_weight, h.num_check_nodes, f.row_ptr))
+            for (size_t j = 0; j < h.num_check_nodes; ++j) // rows allocated one by one (the reference's own layout): gather them
+                f.col_idx.insert(f.col_idx.end(), h.check_nodes[j], h.check_nodes[j] + h.check_nodes_weight[j]);
+        if (!offsets_of(h.bit_nodes, h.bit_nodes_weight, h.num_bit_nodes, f.col_ptr))
+            for (size_t i = 0; i < h.num_bit_nodes; ++i)
+                f.row_idx.insert(f.row_idx.end(), h.bit_nodes[i], h.bit_nodes[i] + h.bit_nodes_weight[i]);
         return f;
     }
 
@@ -67,8 +75,11 @@ namespace qkd_b200
         if (it != reg().codes.end())
             return it->second;
         const flat_matrix f = flatten(h);
+        // loaded matrices are CSR / CSC already: their arrays go to the library as they are
+        const int32_t *col_idx = f.col_idx.empty() && h.num_check_nodes ? h.check_nodes[0] : f.col_idx.data();
+        const int32_t *row_idx = f.row_idx.empty() && h.num_bit_nodes ? h.bit_nodes[0] : f.row_idx.data();
         qlb_code *code = nullptr;
-        check(qlb_code_create(f.n, f.m, f.row_ptr.data(), f.col_idx.data(), f.col_ptr.data(), f.row_idx.data(), &code), "qlb_code_create");
+        check(qlb_code_create(f.n, f.m, f.row_ptr.data(), col_idx, f.col_ptr.data(), row_idx, &code), "qlb_code_create");
         reg().codes.emplace(key_of(h), code);
         return code;
     }

@@ -9,7 +9,8 @@
 
 namespace qkd_b200
 {
-    // Flattened copy of an H_matrix in the C-ABI's input form.
+    // An H_matrix in the C-ABI's input form: the offsets always; the index arrays only when the matrix's rows were allocated one
+    // by one (empty for a matrix from read_*_matrix, whose rows are slices of flat CSR / CSC arrays that are passed as they are).
     struct flat_matrix
     {
         int32_t n = 0, m = 0;

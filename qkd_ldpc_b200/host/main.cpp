@@ -2,6 +2,7 @@
 // in <dir>/alist_sparse_matrices (or dense_matrices), runs the sweep on the GPUs and writes <dir>/results/*.csv.
 // <dir> is argv[1], else $QKD_SOURCE_DIR, else the compile-time SOURCE_DIR, else ".".
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <iostream>
 #include <string>
@@ -32,6 +33,7 @@ std::vector<fs::path> get_file_paths_in_directory(const fs::path &directory_path
 
 // Inspection modes used by the test-suite (no GPU needed):
 //   --dump-matrix <alist|dense> <file>   prints the loaded H_matrix
+//   --time-load <alist|dense> <file>     loads the file, prints seconds, N, M, edges and a checksum of both adjacency halves
 //   --gen <seed> <n> <qber>              prints the exact QBER and Alice's / Bob's keys of one trial
 //   --seeds <seed> <count>               prints raw xoshiro256++ outputs
 //   --peg <n> <m> <dv> <seed> <out> [lim] writes a seeded PEG code as alist (configs[3], configs[4] of BASELINE.json)
@@ -61,6 +63,26 @@ static int inspect(int argc, char **argv)
                 std::cout << " " << h.check_nodes[j][k];
             std::cout << "\n";
         }
+        free_matrix_H(h);
+        return EXIT_SUCCESS;
+    }
+    if (mode == "--time-load" && argc == 4)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        H_matrix h;
+        if (std::string(argv[2]) == "dense")
+            read_dense_matrix(argv[3], h);
+        else
+            read_sparse_alist_matrix(argv[3], h);
+        const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        unsigned long long edges = 0, sum_bits = 0, sum_checks = 0;
+        for (size_t i = 0; i < h.num_bit_nodes; ++i)
+            for (int k = 0; k < h.bit_nodes_weight[i]; ++k, ++edges)
+                sum_bits += static_cast<unsigned long long>(h.bit_nodes[i][k]) * (i + 1);
+        for (size_t j = 0; j < h.num_check_nodes; ++j)
+            for (int k = 0; k < h.check_nodes_weight[j]; ++k)
+                sum_checks += static_cast<unsigned long long>(h.check_nodes[j][k] + 1) * j;
+        std::cout << seconds << " " << h.num_bit_nodes << " " << h.num_check_nodes << " " << edges << " " << sum_bits << " " << sum_checks << "\n";
         free_matrix_H(h);
         return EXIT_SUCCESS;
     }
@@ -95,7 +117,7 @@ static int inspect(int argc, char **argv)
                                      std::strtoull(argv[5], nullptr, 10), argc == 8 ? std::strtoull(argv[7], nullptr, 10) : 4096, argv[6]);
         return EXIT_SUCCESS;
     }
-    std::cerr << "usage: qkd_ldpc_b200_sim [dir] | --peg <n> <m> <col_weight> <seed> <out.alist> [bfs_limit] | --dump-matrix <alist|dense> <file> | --gen <seed> <n> <qber> | --seeds <seed> <count>\n";
+    std::cerr << "usage: qkd_ldpc_b200_sim [dir] | --peg <n> <m> <col_weight> <seed> <out.alist> [bfs_limit] | --dump-matrix <alist|dense> <file> | --time-load <alist|dense> <file> | --gen <seed> <n> <qber> | --seeds <seed> <count>\n";
     return EXIT_FAILURE;
 }
 

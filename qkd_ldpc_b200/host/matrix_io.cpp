@@ -1,12 +1,16 @@
-// Parity-check matrix files -> H_matrix, and the key helpers that stay on the host.
+// Parity-check matrix files -> H_matrix (flat CSR / CSC arrays behind the reference's row pointers), and the key helpers that
+// stay on the host.
 // Mirrors (same signatures, validation and messages): reference src/array_and_matrix_operations.cpp
 //   read_sparse_alist_matrix :109-292, read_dense_matrix :295-421, free_matrix_H :88-94, arrays_equal :96-106,
 //   generate_random_bit_array :424-431, introduce_errors :434-460.
 #include <algorithm>
+#include <cstring>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <random>
-#include <sstream>
+#include <set>
 #include <stdexcept>
 
 #include "device_bridge.hpp"
@@ -14,30 +18,98 @@
 
 namespace
 {
-    using table = std::vector<std::vector<int>>;
-
-    // Every line of the file as a row of integers (tokens that are not integers end the row, as `iss >> int` does).
-    table read_int_rows(const fs::path &path, bool binary_only)
+    // ---- text scanning ------------------------------------------------------------------------------------------------------
+    // The reference reads a file line by line and each line with `iss >> int` (src/array_and_matrix_operations.cpp:119-141):
+    // integers separated by white space, the first token that is not an integer ends the row. Here the file is read once into
+    // one buffer and scanned in place; rows are delivered value by value to a callback, so nothing is held per line -- the
+    // adjacency lists go straight into two flat arrays (CSR for the checks, CSC for the bits).
+    struct text_file
     {
-        std::ifstream file(path);
-        if (!file.is_open())
-            throw std::runtime_error("Failed to open file: " + path.string());
-        table rows;
-        std::string line;
-        while (std::getline(file, line))
+        std::string data;
+        size_t lines = 0; // as std::getline counts them: a final line without '\n' counts, an empty tail after the last '\n' does not
+        explicit text_file(const fs::path &path)
         {
-            std::istringstream iss(line);
-            std::vector<int> row;
-            for (int v; iss >> v;)
-            {
-                if (binary_only && v != 0 && v != 1)
-                    throw std::runtime_error("Parity check matrix can only take values 0 or 1.");
-                row.push_back(v);
-            }
-            rows.push_back(std::move(row));
+            std::ifstream file(path, std::ios::binary);
+            if (!file.is_open())
+                throw std::runtime_error("Failed to open file: " + path.string());
+            file.seekg(0, std::ios::end);
+            const std::streamoff size = file.tellg();
+            file.seekg(0, std::ios::beg);
+            data.resize(size > 0 ? static_cast<size_t>(size) : 0);
+            if (!data.empty())
+                file.read(data.data(), static_cast<std::streamsize>(data.size()));
+            lines = static_cast<size_t>(std::count(data.begin(), data.end(), '\n')) + ((!data.empty() && data.back() != '\n') ? 1 : 0);
+            if (lines == 0)
+                throw std::runtime_error("File is empty or cannot be read properly: " + path.string());
         }
-        if (rows.empty())
-            throw std::runtime_error("File is empty or cannot be read properly: " + path.string());
+    };
+
+    struct line_cursor
+    {
+        const char *p, *end;
+        explicit line_cursor(const text_file &f) : p(f.data.data()), end(f.data.data() + f.data.size()) {}
+        // Scans the next line, calling on_value(v) for every integer `iss >> int` would extract from it; returns how many.
+        template <typename F>
+        size_t next(F &&on_value)
+        {
+            const char *eol = static_cast<const char *>(std::memchr(p, '\n', static_cast<size_t>(end - p)));
+            const char *stop = eol ? eol : end;
+            size_t count = 0;
+            const char *q = p;
+            for (;;)
+            {
+                while (q < stop && (*q == ' ' || *q == '\t' || *q == '\r' || *q == '\v' || *q == '\f'))
+                    ++q;
+                if (q >= stop)
+                    break;
+                bool negative = false;
+                if (*q == '+' || *q == '-')
+                {
+                    negative = *q == '-';
+                    ++q;
+                }
+                if (q >= stop || *q < '0' || *q > '9')
+                    break; // not an integer: the extraction fails and the row ends here
+                long long v = 0;
+                bool overflow = false;
+                while (q < stop && *q >= '0' && *q <= '9')
+                {
+                    v = v * 10 + (*q - '0');
+                    if (v > 2147483648LL)
+                        overflow = true, v = 2147483648LL;
+                    ++q;
+                }
+                if (negative)
+                    v = -v;
+                if (overflow || v > 2147483647LL || v < -2147483648LL)
+                    break; // out of int's range: failbit, the row ends
+                on_value(static_cast<int>(v));
+                ++count;
+            }
+            p = eol ? eol + 1 : end;
+            return count;
+        }
+    };
+
+    // ---- storage --------------------------------------------------------------------------------------------------------------
+    // H_matrix keeps the reference's shape (int ** rows), but the rows of a loaded matrix are slices of ONE array per direction:
+    // check_nodes[j] = csr + row_ptr[j], bit_nodes[i] = csc + col_ptr[i]. device_bridge hands those arrays to qlb_code_create
+    // without copying. The arenas are remembered here so that free_matrix_H knows a loaded matrix from one whose rows a caller
+    // allocated one by one (the reference's own layout, still accepted everywhere).
+    std::mutex g_arena_mu;
+    std::set<const int *> g_arenas;
+
+    int **slice_rows(int *arena, const int *weights, size_t count)
+    {
+        int **rows = new int *[count];
+        size_t at = 0;
+        for (size_t i = 0; i < count; ++i)
+        {
+            rows[i] = arena + at;
+            at += static_cast<size_t>(weights[i]);
+        }
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        g_arenas.insert(arena);
         return rows;
     }
 
@@ -45,14 +117,32 @@ namespace
     {
         if (!rows)
             return;
-        for (size_t i = 0; i < count; ++i)
-            delete[] rows[i];
+        bool arena = false;
+        if (count > 0)
+        {
+            std::lock_guard<std::mutex> lk(g_arena_mu);
+            arena = g_arenas.erase(rows[0]) > 0;
+        }
+        if (arena)
+            delete[] rows[0];
+        else
+            for (size_t i = 0; i < count; ++i)
+                delete[] rows[i];
         delete[] rows;
     }
 
     bool all_equal(const int *w, size_t n)
     {
         return std::all_of(w, w + n, [&](int v) { return v == w[0]; });
+    }
+
+    // one array for `count` lists of the given weights (at least one element, so that the arena has an address of its own)
+    int *new_arena(const int *weights, size_t count)
+    {
+        size_t total = 0;
+        for (size_t i = 0; i < count; ++i)
+            total += static_cast<size_t>(std::max(weights[i], 0));
+        return new int[std::max<size_t>(total, 1)];
     }
 }
 
@@ -73,16 +163,25 @@ bool arrays_equal(const int *const array1, const int *const array2, const size_t
 
 void read_sparse_alist_matrix(const fs::path &matrix_path, H_matrix &matrix_out)
 {
-    const table t = read_int_rows(matrix_path, false);
+    const text_file file(matrix_path);
     const std::string where = matrix_path.string();
-    if (t.size() < 4)
+    if (file.lines < 4)
         throw std::runtime_error("Insufficient data in the file: " + where);
-    if (t[0].size() != 2 || t[1].size() != 2)
+    line_cursor cur(file);
+    int dims[2] = {0, 0}, max_w[2] = {0, 0};
+    size_t k = 0;
+    const size_t dims_count = cur.next([&](int v) { if (k < 2) dims[k] = v; ++k; });
+    k = 0;
+    const size_t maxw_count = cur.next([&](int v) { if (k < 2) max_w[k] = v; ++k; });
+    if (dims_count != 2 || maxw_count != 2)
         throw std::runtime_error("File format does not match the alist format: " + where);
+    std::vector<int> bit_w, check_w; // third and fourth line
+    cur.next([&](int v) { bit_w.push_back(v); });
+    cur.next([&](int v) { check_w.push_back(v); });
 
-    const size_t n = t[0][0], m = t[0][1];
-    const size_t n_listed = t[2].size(), m_listed = t[3].size();
-    if (t.size() < 4 + n_listed + m_listed)
+    const size_t n = static_cast<size_t>(dims[0]), m = static_cast<size_t>(dims[1]);
+    const size_t n_listed = bit_w.size(), m_listed = check_w.size();
+    if (file.lines < 4 + n_listed + m_listed)
         throw std::runtime_error("Insufficient data in the file: " + where);
     if (n != n_listed)
         throw std::runtime_error("Number of columns '" + std::to_string(n) + "' is not the same as the length of the third line '" +
@@ -91,66 +190,84 @@ void read_sparse_alist_matrix(const fs::path &matrix_path, H_matrix &matrix_out)
         throw std::runtime_error("Number of rows '" + std::to_string(m) + "' is not the same as the length of the fourth line '" +
                                  std::to_string(m_listed) + "'. File: " + where);
 
-    // the number of non-zero entries of every list must equal the declared weight
-    auto check_weights = [&](size_t first_line, const std::vector<int> &weights, const char *which)
+    // One pass over the list lines: the first `weight` entries of a line (1-based, trailing zero padding never looked at) go
+    // straight to their place in the flat array, while the line's non-zero entries are counted against the declared weight.
+    std::unique_ptr<int[]> csc(new_arena(bit_w.data(), n)), csr(new_arena(check_w.data(), m));
+    auto read_lists = [&](const std::vector<int> &weights, int *arena, size_t first_line, const char *which)
     {
+        size_t at = 0;
         for (size_t i = 0; i < weights.size(); ++i)
         {
-            const auto &row = t[first_line + i];
-            const size_t nz = std::count_if(row.begin(), row.end(), [](int v) { return v != 0; });
-            if (nz != static_cast<size_t>(weights[i]))
+            const int w = weights[i];
+            size_t nz = 0;
+            int taken = 0;
+            cur.next([&](int v)
+                     {
+                         nz += v != 0;
+                         if (taken < w)
+                             arena[at + taken++] = v - 1;
+                     });
+            if (nz != static_cast<size_t>(w))
                 throw std::runtime_error("Number of non-zero elements '" + std::to_string(nz) + "' in the line '" +
                                          std::to_string(first_line + i + 1) + "' does not match the weight in the " + which + " line '" +
-                                         std::to_string(weights[i]) + "'. File: " + where);
+                                         std::to_string(w) + "'. File: " + where);
+            at += static_cast<size_t>(w);
         }
     };
-    check_weights(4, t[2], "third");
-    check_weights(4 + n, t[3], "fourth");
+    read_lists(bit_w, csc.get(), 4, "third");
+    read_lists(check_w, csr.get(), 4 + n, "fourth");
 
     H_matrix h;
     h.num_bit_nodes = n;
     h.num_check_nodes = m;
-    h.max_bit_nodes_weight = t[1][0];
-    h.max_check_nodes_weight = t[1][1];
+    h.max_bit_nodes_weight = max_w[0];
+    h.max_check_nodes_weight = max_w[1];
     h.bit_nodes_weight = new int[n];
     h.check_nodes_weight = new int[m];
-    std::copy(t[2].begin(), t[2].end(), h.bit_nodes_weight);
-    std::copy(t[3].begin(), t[3].end(), h.check_nodes_weight);
+    std::copy(bit_w.begin(), bit_w.end(), h.bit_nodes_weight);
+    std::copy(check_w.begin(), check_w.end(), h.check_nodes_weight);
     h.is_regular = all_equal(h.bit_nodes_weight, n) && all_equal(h.check_nodes_weight, m);
-
-    // lists are 1-based in the file and read up to the node's weight (trailing zero padding is never looked at)
-    auto fill = [&](size_t first_line, const int *weights, size_t count)
-    {
-        int **rows = new int *[count];
-        for (size_t i = 0; i < count; ++i)
-        {
-            rows[i] = new int[weights[i]];
-            for (int k = 0; k < weights[i]; ++k)
-                rows[i][k] = t[first_line + i][k] - 1;
-        }
-        return rows;
-    };
-    h.bit_nodes = fill(4, h.bit_nodes_weight, n);
-    h.check_nodes = fill(4 + n, h.check_nodes_weight, m);
+    h.bit_nodes = slice_rows(csc.release(), h.bit_nodes_weight, n);
+    h.check_nodes = slice_rows(csr.release(), h.check_nodes_weight, m);
     matrix_out = h;
 }
 
 void read_dense_matrix(const fs::path &matrix_path, H_matrix &matrix_out)
 {
-    const table t = read_int_rows(matrix_path, true);
+    const text_file file(matrix_path);
     const std::string where = matrix_path.string();
-    for (const auto &row : t)
-        if (row.size() != t[0].size())
-            throw std::runtime_error("Different lengths of rows in a matrix. File: " + where);
-
-    const size_t n = t[0].size(), m = t.size();
-    std::vector<int> col_w(n, 0), row_w(m, 0);
-    for (size_t j = 0; j < m; ++j)
-        for (size_t i = 0; i < n; ++i)
-        {
-            col_w[i] += t[j][i];
-            row_w[j] += t[j][i];
-        }
+    // One pass: the positions of the ones of each row ARE the CSR half; column weights are counted on the way.
+    std::vector<int> csr, row_w, col_w;
+    csr.reserve(file.data.size() / 8);
+    size_t n = 0;
+    bool ragged = false;
+    line_cursor cur(file);
+    for (size_t j = 0; j < file.lines; ++j)
+    {
+        int column = 0, ones = 0;
+        cur.next([&](int v)
+                 {
+                     if (v != 0 && v != 1)
+                         throw std::runtime_error("Parity check matrix can only take values 0 or 1.");
+                     if (v == 1)
+                     {
+                         csr.push_back(column);
+                         ++ones;
+                         if (static_cast<size_t>(column) >= col_w.size())
+                             col_w.resize(static_cast<size_t>(column) + 1, 0);
+                         ++col_w[static_cast<size_t>(column)];
+                     }
+                     ++column;
+                 });
+        if (j == 0)
+            n = static_cast<size_t>(column);
+        ragged |= static_cast<size_t>(column) != n;
+        row_w.push_back(ones);
+    }
+    if (ragged)
+        throw std::runtime_error("Different lengths of rows in a matrix. File: " + where);
+    const size_t m = row_w.size();
+    col_w.resize(n, 0);
     for (size_t i = 0; i < n; ++i)
         if (col_w[i] <= 0)
             throw std::runtime_error("Column '" + std::to_string(i + 1) + "' weight cannot be equal to or less than zero. File: " + where);
@@ -165,29 +282,22 @@ void read_dense_matrix(const fs::path &matrix_path, H_matrix &matrix_out)
     h.check_nodes_weight = new int[m];
     std::copy(col_w.begin(), col_w.end(), h.bit_nodes_weight);
     std::copy(row_w.begin(), row_w.end(), h.check_nodes_weight);
-    h.max_bit_nodes_weight = *std::max_element(col_w.begin(), col_w.end());
-    h.max_check_nodes_weight = *std::max_element(row_w.begin(), row_w.end());
+    h.max_bit_nodes_weight = n ? *std::max_element(col_w.begin(), col_w.end()) : 0;
+    h.max_check_nodes_weight = m ? *std::max_element(row_w.begin(), row_w.end()) : 0;
     h.is_regular = all_equal(h.bit_nodes_weight, n) && all_equal(h.check_nodes_weight, m);
 
-    // ascending neighbour lists in both directions
-    h.bit_nodes = new int *[n];
+    // CSC by a counting sort of the CSR entries: rows are visited in ascending order, so every bit's list comes out ascending
+    int *csr_arena = new_arena(h.check_nodes_weight, m), *csc_arena = new_arena(h.bit_nodes_weight, n);
+    std::copy(csr.begin(), csr.end(), csr_arena);
+    std::vector<size_t> fill(n + 1, 0);
     for (size_t i = 0; i < n; ++i)
-    {
-        h.bit_nodes[i] = new int[col_w[i]];
-        int k = 0;
-        for (size_t j = 0; j < m; ++j)
-            if (t[j][i] == 1)
-                h.bit_nodes[i][k++] = static_cast<int>(j);
-    }
-    h.check_nodes = new int *[m];
+        fill[i + 1] = fill[i] + static_cast<size_t>(col_w[i]);
+    size_t at = 0;
     for (size_t j = 0; j < m; ++j)
-    {
-        h.check_nodes[j] = new int[row_w[j]];
-        int k = 0;
-        for (size_t i = 0; i < n; ++i)
-            if (t[j][i] == 1)
-                h.check_nodes[j][k++] = static_cast<int>(i);
-    }
+        for (int k2 = 0; k2 < row_w[j]; ++k2)
+            csc_arena[fill[static_cast<size_t>(csr[at++])]++] = static_cast<int>(j);
+    h.bit_nodes = slice_rows(csc_arena, h.bit_nodes_weight, n);
+    h.check_nodes = slice_rows(csr_arena, h.check_nodes_weight, m);
     matrix_out = h;
 }
 
