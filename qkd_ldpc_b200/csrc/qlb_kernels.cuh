@@ -28,6 +28,24 @@ namespace qlb
 {
     constexpr int kMaxCW = 64;
 
+    // -DQLB_BOUNDS_CHECK: the kernels test the indices they are about to use (message slots, frame columns, scratch offsets) and
+    // trap on the first one out of range -- the stand-in for compute-sanitizer's memcheck, which is closed on the B200 pool
+    // (profiles/r02_compute_sanitizer_closed.log). Built and run by scripts/bounds_check_build.sh; off in the product build.
+#ifdef QLB_BOUNDS_CHECK
+#define QLB_CHECK_INDEX(i, n)                                                                                             \
+    do                                                                                                                    \
+    {                                                                                                                     \
+        if (!((unsigned long long)(i) < (unsigned long long)(n)))                                                         \
+        {                                                                                                                 \
+            printf("QLB_BOUNDS_CHECK %s:%d: %s = %llu not below %s = %llu (block %d thread %d)\n", __FILE__, __LINE__, #i, \
+                   (unsigned long long)(i), #n, (unsigned long long)(n), (int)blockIdx.x, (int)threadIdx.x);               \
+            __trap();                                                                                                     \
+        }                                                                                                                 \
+    } while (0)
+#else
+#define QLB_CHECK_INDEX(i, n) ((void)0)
+#endif
+
     enum Tier
     {
         kTierSmemAll = 0, // messages + bit_slots + zedge + bit arrays in shared memory (16-bit slot indices)

@@ -167,6 +167,9 @@ namespace qlb
         const DecodeArgs &args;
         __device__ __forceinline__ uint32_t operator()(int k) const { return args.code.base4[k]; }
     };
+#ifdef QLB_BOUNDS_CHECK
+    static __device__ uint32_t g_bounds_msg_bytes = 0xFFFFFFFFu; // 4 * slots of the code being decoded (set by the launcher in bounds-check builds)
+#endif
     struct BaseFromSmem
     {
         const uint32_t *base4;
@@ -190,6 +193,7 @@ namespace qlb
 #pragma unroll
             for (int k = 0; k < W; ++k)
             {
+                QLB_CHECK_INDEX((size_t)(row - msg_bytes) + base4(k), g_bounds_msg_bytes);
                 v[k] = *reinterpret_cast<const float *>(row + base4(k));
                 xr ^= __float_as_uint(v[k]);
             }
@@ -254,7 +258,10 @@ namespace qlb
                 sl[a] = 4u * (uint32_t)bs[a * n];
 #pragma unroll
             for (int a = 0; a < kBW; ++a)
+            {
+                QLB_CHECK_INDEX(sl[a], g_bounds_msg_bytes);
                 c[a] = *reinterpret_cast<const float *>(msg_bytes + sl[a]);
+            }
             float total = prior;
 #pragma unroll
             for (int a = 0; a < kBW; ++a)

@@ -53,9 +53,15 @@ namespace qlb
         double *smem;
         double *gmem; // slot s >= smem_slots is gmem[s - smem_slots]
         uint32_t smem_slots;
-        __device__ __forceinline__ double ld(uint32_t slot) const { return slot < smem_slots ? smem[slot] : gmem[slot - smem_slots]; }
+        uint32_t slots; // read by bounds-check builds only
+        __device__ __forceinline__ double ld(uint32_t slot) const
+        {
+            QLB_CHECK_INDEX(slot, slots);
+            return slot < smem_slots ? smem[slot] : gmem[slot - smem_slots];
+        }
         __device__ __forceinline__ void st(uint32_t slot, double v) const
         {
+            QLB_CHECK_INDEX(slot, slots);
             if (slot < smem_slots)
                 smem[slot] = v;
             else
@@ -100,6 +106,11 @@ namespace qlb
         for (int k = 0; k < W; ++k)
         {
             const uint32_t slot = s_base(k) + p;
+            QLB_CHECK_INDEX(slot, msg.slots);
+            if (kTail != 3 && k < W - kTail)
+                QLB_CHECK_INDEX(slot, msg.smem_slots); // a row the group table promises to shared memory ...
+            if (kTail != 3 && k >= W - kTail)
+                QLB_CHECK_INDEX(msg.smem_slots, slot + 1u); // ... and one it promises to the global tail
             v[k] = kTail == 3 ? msg.ld(slot) : (k < W - kTail ? msg.smem[slot] : gm[slot]);
         }
         Math::template check_fast<W>(v, syn, thr_eff, want_inf);
@@ -157,6 +168,7 @@ namespace qlb
         Split64 msg;
         msg.smem = reinterpret_cast<double *>(smem);
         msg.smem_slots = smem_slots;
+        msg.slots = (uint32_t)code.slots;
         msg.gmem = reinterpret_cast<double *>(args.scratch + (size_t)blockIdx.x * args.scratch_stride);
         unsigned char *tail = smem + (size_t)smem_slots * 8;
         uint32_t *s_bob = reinterpret_cast<uint32_t *>(tail);
@@ -336,7 +348,10 @@ namespace qlb
                         {
 #pragma unroll
                             for (int a = 0; a < kBW; ++a)
+                            {
+                                QLB_CHECK_INDEX(sl[a], msg.smem_slots); // a `fast` group never leaves shared memory
                                 c[a] = msg.smem[sl[a]];
+                            }
                             double total = prior;
 #pragma unroll
                             for (int a = 0; a < kBW; ++a)

@@ -116,6 +116,8 @@ namespace qlb
 #pragma unroll
         for (int k = 0; k < W; ++k)
         {
+            QLB_CHECK_INDEX(code.base[k] + p, code.slots);
+            QLB_CHECK_INDEX(p, code.cnt[k]);
             row[k] = msg + VEC * lane + (size_t)((code.base[k] + p) * row_stride); // 32-bit product (slots * row_stride < 2^32)
             float t[VEC];
             VecIO<float, VEC>::load(row[k], t);
@@ -181,10 +183,13 @@ namespace qlb
 #pragma unroll
         for (int k = 0; k < W; ++k)
         {
+            QLB_CHECK_INDEX(code.base[k] + p, code.slots);
+            QLB_CHECK_INDEX(p, code.cnt[k]);
             row[k] = msg + VEC * lane + (size_t)((code.base[k] + p) * row_stride); // 32-bit product (slots * row_stride < 2^32)
             double t[VEC];
             VecIO<double, VEC>::load(row[k], t);
             const uint32_t bit = code.col_of_slot32[code.base[k] + p];
+            QLB_CHECK_INDEX(bit, code.n);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
             {

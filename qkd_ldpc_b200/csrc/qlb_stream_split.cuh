@@ -113,6 +113,8 @@ namespace qlb
         const uint32_t bu = g / (uint32_t)B, gb = g % (uint32_t)B;
         const SplitSmall cv = split_small_carve(code.n, code.m, vec);
         unsigned char *p = st.bundles + (size_t)bu * st.bundle_stride;
+        QLB_CHECK_INDEX(g, st.n_groups);
+        QLB_CHECK_INDEX(align_up((size_t)code.slots * B * G * sizeof(Real), 256) + (size_t)(gb + 1) * cv.total - 1, st.bundle_stride);
         unsigned char *small = p + align_up((size_t)code.slots * B * G * sizeof(Real), 256) + (size_t)gb * cv.total;
         SplitGroup<Real> r;
         r.msg = reinterpret_cast<Real *>(p) + (size_t)gb * G;
@@ -266,7 +268,10 @@ namespace qlb
                 }
 #pragma unroll
                 for (int a = 0; a < kBW; ++a)
+                {
+                    QLB_CHECK_INDEX(code.bit_slots32[(size_t)a * n + i], code.slots);
                     VecIO<Real, VEC>::store(sg.msg + VEC * lane + (size_t)(code.bit_slots32[(size_t)a * n + i] * sg.row_stride), pv);
+                }
                 if (lane == 0)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j)
@@ -406,6 +411,7 @@ namespace qlb
                         {
                             const int l = __ffs(done) - 1;
                             done &= done - 1;
+                            QLB_CHECK_INDEX(st.fmap[(size_t)g * G + VEC * l + j], args.n_frames);
                             args.iterations[st.fmap[(size_t)g * G + VEC * l + j]] = (uint32_t)it;
                         }
                     }
@@ -437,7 +443,11 @@ namespace qlb
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int a = 0; a < kBW; ++a)
+            {
+                QLB_CHECK_INDEX(bit[u], n);
+                QLB_CHECK_INDEX(code.bit_slots32[(size_t)a * n + bit[u]], code.slots);
                 row[u][a] = sg.msg + VEC * lane + (size_t)(code.bit_slots32[(size_t)a * n + bit[u]] * sg.row_stride);
+            }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -629,6 +639,7 @@ namespace qlb
                         uint8_t r = (st.succ[g * 4 + j] >> lane) & 1u ? 1 : 0;
                         if (kReconcile && !((differs >> j) & 1u))
                             r |= 2;
+                        QLB_CHECK_INDEX(fr[j], args.n_frames);
                         args.result[fr[j]] = r;
                         it_sum += args.iterations[fr[j]];
                     }
@@ -754,7 +765,11 @@ namespace qlb
             {
                 const uint32_t k1 = min(live, k0 + kRepackStage);
                 for (uint32_t k = k0 + threadIdx.x; k < k1; k += kRepackThreads)
+                {
+                    QLB_CHECK_INDEX(st.src_of[k], (unsigned)st.n_groups * G);
+                    QLB_CHECK_INDEX(k, st.src_of[k] + 1u); // in place: a live column never moves to a later position
                     s_val[k - k0] = *at(slot, st.src_of[k]);
+                }
                 __syncthreads();
                 for (uint32_t k = k0 + threadIdx.x; k < k1; k += kRepackThreads)
                     *at(slot, k) = s_val[k - k0];

@@ -19,6 +19,10 @@ namespace
         long long grid = ctx->sm_count; // one resident CTA per SM
         if (grid > args.n_frames)
             grid = args.n_frames;
+#ifdef QLB_BOUNDS_CHECK
+        const uint32_t msg_bytes = 4u * (uint32_t)args.code.slots;
+        QLB_CUDA(cudaMemcpyToSymbolAsync(g_bounds_msg_bytes, &msg_bytes, 4, 0, cudaMemcpyHostToDevice, ctx->stream));
+#endif
         QLB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
         args.queue = ctx->d_counters;
         args.iter_total = ctx->d_counters + 1;
