@@ -228,6 +228,11 @@ int qlb_test_f64_math(qlb_ctx *ctx, int op, int64_t n, const double *a, const do
  * qkd_ldpc_b200/sweep.py.)
  */
 int qlb_stats_allreduce(qlb_ctx *const *ctxs, int n_ctx, uint64_t *const *vectors, size_t count);
+/* Creates (and keeps) the NCCL communicators qlb_stats_allreduce will use for contexts on these devices (in this order), and
+ * nothing else: no collective runs. Communicator set-up takes seconds on an 8-GPU box; a sweep scheduler calls this from a side
+ * thread as it starts, so that the set-up runs beside the CUDA start-up of the devices and the all-reduce at the end of the
+ * sweep finds the communicators ready. Optional: qlb_stats_allreduce creates them itself when they are missing. */
+int qlb_stats_comm_prepare(const int32_t *devices, int n_devices);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "qlb_ctx_create", "qlb_ctx_destroy", "qlb_ctx_device", "qlb_ctx_sm_count", "qlb_ctx_stream", "qlb_ctx_synchronize",
     "qlb_ctx_counters", "qlb_ctx_timer_start", "qlb_ctx_timer_stop",
     "qlb_syndrome_batch", "qlb_syndrome_batch_packed", "qlb_sum_product_batch", "qlb_sum_product_trace",
-    "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device", "qlb_stats_allreduce",
+    "qlb_reconcile_batch", "qlb_reconcile_batch_packed", "qlb_reconcile_device", "qlb_stats_allreduce", "qlb_stats_comm_prepare",
     "qlb_generate_batch_packed", "qlb_generate_device", "qlb_run_trials", "qlb_test_f64_math",
 ]
 

@@ -824,42 +824,100 @@ extern "C"
     }
 
     // ---- statistics all-reduce over the GPUs of this process (NCCL, loaded lazily) ---------------------------------------
-    int qlb_stats_allreduce(qlb_ctx *const *ctxs, int n_ctx, uint64_t *const *vectors, size_t count)
+    namespace
     {
-        if (!ctxs || !vectors || n_ctx < 1 || count == 0)
-            return fail(QLB_ERR_INVALID, "qlb_stats_allreduce: bad arguments");
-        typedef void *comm_t;
-        typedef int (*init_all_t)(comm_t *, int, const int *);
-        typedef int (*allreduce_t)(const void *, void *, size_t, int, int, comm_t, cudaStream_t);
-        typedef int (*group_t)(void);
-        typedef const char *(*errstr_t)(int);
+        typedef void *nccl_comm_t;
         struct nccl_api
         {
+            typedef int (*init_all_t)(nccl_comm_t *, int, const int *);
+            typedef int (*allreduce_t)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+            typedef int (*group_t)(void);
+            typedef const char *(*errstr_t)(int);
             void *lib = nullptr;
             init_all_t init_all = nullptr;
             allreduce_t allreduce = nullptr;
             group_t group_start = nullptr, group_end = nullptr;
             errstr_t errstr = nullptr;
-            std::map<std::vector<int>, std::vector<comm_t>> comms;
+            std::map<std::vector<int>, std::vector<nccl_comm_t>> comms;
             std::mutex mu;
+            int fail_with(int rc, const char *what) const { return fail(QLB_ERR_NCCL, std::string(what) + ": " + (errstr ? errstr(rc) : "NCCL error")); }
         };
-        static nccl_api api;
-        std::lock_guard<std::mutex> lk(api.mu);
-        if (!api.lib)
+        nccl_api g_nccl;
+
+        // The communicators of a device list (created once, kept for the life of the process). Caller holds g_nccl.mu.
+        int nccl_comms_for(const std::vector<int> &devs, std::vector<nccl_comm_t> **out)
         {
-            api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            const int n_ctx = (int)devs.size();
+            nccl_api &api = g_nccl;
             if (!api.lib)
-                return fail(QLB_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
-            api.init_all = (init_all_t)dlsym(api.lib, "ncclCommInitAll");
-            api.allreduce = (allreduce_t)dlsym(api.lib, "ncclAllReduce");
-            api.group_start = (group_t)dlsym(api.lib, "ncclGroupStart");
-            api.group_end = (group_t)dlsym(api.lib, "ncclGroupEnd");
-            api.errstr = (errstr_t)dlsym(api.lib, "ncclGetErrorString");
-            if (!api.init_all || !api.allreduce || !api.group_start || !api.group_end)
-                return fail(QLB_ERR_NCCL, "libnccl.so.2 lacks the expected entry points");
+            {
+                api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+                if (!api.lib)
+                    return fail(QLB_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+                api.init_all = (nccl_api::init_all_t)dlsym(api.lib, "ncclCommInitAll");
+                api.allreduce = (nccl_api::allreduce_t)dlsym(api.lib, "ncclAllReduce");
+                api.group_start = (nccl_api::group_t)dlsym(api.lib, "ncclGroupStart");
+                api.group_end = (nccl_api::group_t)dlsym(api.lib, "ncclGroupEnd");
+                api.errstr = (nccl_api::errstr_t)dlsym(api.lib, "ncclGetErrorString");
+                if (!api.init_all || !api.allreduce || !api.group_start || !api.group_end)
+                    return fail(QLB_ERR_NCCL, "libnccl.so.2 lacks the expected entry points");
+            }
+            auto it = api.comms.find(devs);
+            if (it == api.comms.end())
+            {
+                std::vector<nccl_comm_t> comms(n_ctx, nullptr);
+                int rc = api.init_all(comms.data(), n_ctx, devs.data());
+                if (rc != 0)
+                    return api.fail_with(rc, "ncclCommInitAll");
+                // NCCL connects its channels lazily, inside the first collective (0.1 ... 0.9 s measured on 2 GPUs): run one tiny
+                // all-reduce now, while the set-up is still off the sweep's critical path
+                std::vector<void *> buf(n_ctx, nullptr);
+                std::vector<cudaStream_t> str(n_ctx, nullptr);
+                for (int g = 0; g < n_ctx; ++g)
+                {
+                    QLB_CUDA(cudaSetDevice(devs[g]));
+                    QLB_CUDA(cudaMalloc(&buf[g], 64));
+                    QLB_CUDA(cudaMemset(buf[g], 0, 64));
+                    QLB_CUDA(cudaStreamCreateWithFlags(&str[g], cudaStreamNonBlocking));
+                }
+                rc = api.group_start();
+                for (int g = 0; g < n_ctx && rc == 0; ++g)
+                {
+                    QLB_CUDA(cudaSetDevice(devs[g]));
+                    rc = api.allreduce(buf[g], buf[g], 8, /*ncclUint64*/ 5, /*ncclSum*/ 0, comms[g], str[g]);
+                }
+                const int rc_end = api.group_end();
+                for (int g = 0; g < n_ctx; ++g)
+                {
+                    QLB_CUDA(cudaSetDevice(devs[g]));
+                    QLB_CUDA(cudaStreamSynchronize(str[g]));
+                    cudaStreamDestroy(str[g]);
+                    cudaFree(buf[g]);
+                }
+                if (rc != 0 || rc_end != 0)
+                    return api.fail_with(rc != 0 ? rc : rc_end, "first ncclAllReduce");
+                it = api.comms.emplace(devs, comms).first;
+            }
+            *out = &it->second;
+            return QLB_OK;
         }
-        auto nccl_fail = [&](int rc, const char *what)
-        { return fail(QLB_ERR_NCCL, std::string(what) + ": " + (api.errstr ? api.errstr(rc) : "NCCL error")); };
+    }
+
+    int qlb_stats_comm_prepare(const int32_t *devices, int n_devices)
+    {
+        if (!devices || n_devices < 1)
+            return fail(QLB_ERR_INVALID, "qlb_stats_comm_prepare: bad arguments");
+        std::lock_guard<std::mutex> lk(g_nccl.mu);
+        std::vector<nccl_comm_t> *comms = nullptr;
+        return nccl_comms_for(std::vector<int>(devices, devices + n_devices), &comms);
+    }
+
+    int qlb_stats_allreduce(qlb_ctx *const *ctxs, int n_ctx, uint64_t *const *vectors, size_t count)
+    {
+        if (!ctxs || !vectors || n_ctx < 1 || count == 0)
+            return fail(QLB_ERR_INVALID, "qlb_stats_allreduce: bad arguments");
+        nccl_api &api = g_nccl;
+        std::lock_guard<std::mutex> lk(api.mu);
         std::vector<int> devs;
         for (int g = 0; g < n_ctx; ++g)
         {
@@ -867,15 +925,10 @@ extern "C"
                 return fail(QLB_ERR_INVALID, "qlb_stats_allreduce: null context or vector");
             devs.push_back(ctxs[g]->device);
         }
-        auto it = api.comms.find(devs);
-        if (it == api.comms.end())
-        {
-            std::vector<comm_t> comms(n_ctx, nullptr);
-            const int rc = api.init_all(comms.data(), n_ctx, devs.data());
-            if (rc != 0)
-                return nccl_fail(rc, "ncclCommInitAll");
-            it = api.comms.emplace(devs, comms).first;
-        }
+        std::vector<nccl_comm_t> *comms = nullptr;
+        if (const int rc0 = nccl_comms_for(devs, &comms))
+            return rc0;
+        auto nccl_fail = [&](int rc, const char *what) { return api.fail_with(rc, what); };
         const size_t bytes = count * sizeof(uint64_t);
         for (int g = 0; g < n_ctx; ++g)
         {
@@ -889,7 +942,7 @@ extern "C"
         for (int g = 0; g < n_ctx; ++g)
         {
             QLB_CUDA(cudaSetDevice(ctxs[g]->device));
-            rc = api.allreduce(ctxs[g]->in_q.p, ctxs[g]->in_q.p, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, it->second[g], ctxs[g]->stream);
+            rc = api.allreduce(ctxs[g]->in_q.p, ctxs[g]->in_q.p, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, (*comms)[g], ctxs[g]->stream);
             if (rc != 0)
             {
                 api.group_end();

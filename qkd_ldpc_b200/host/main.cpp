@@ -169,7 +169,8 @@ int main(int argc, char **argv)
         qkd_b200::write_report(qkd_b200::last_sweep_report(), root / "results");
         const auto &rep = qkd_b200::last_sweep_report();
         std::cout << "frames " << rep.frames << ", frame-iterations " << rep.frame_iterations << ", " << rep.gpus << " GPU(s), " << rep.seconds_total
-                  << " s total (" << rep.seconds_startup << " s CUDA start-up, " << rep.seconds_device << " s in device calls per worker): "
+                  << " s total (" << rep.seconds_startup << " s start-up = CUDA contexts beside " << rep.seconds_comm_setup << " s of NCCL communicator set-up; " << rep.seconds_device
+                  << " s in device calls per worker, " << rep.seconds_reduce << " s all-reduce): "
                   << rep.frames / rep.seconds_total << " frames/s overall, " << rep.frames / std::max(1e-9, rep.seconds_total - rep.seconds_startup)
                   << " frames/s once the GPUs are up\n";
     }

@@ -164,7 +164,9 @@ namespace qkd_b200
     {
         double seconds_total{};
         double seconds_device{};
-        double seconds_startup{}; // from entry until every GPU worker holds its context (driver + context initialisation)
+        double seconds_startup{}; // from entry until every GPU worker holds its context and the communicators exist (driver + context + NCCL initialisation)
+        double seconds_comm_setup{}; // NCCL communicator set-up on the side thread (part of the start-up); 0 without a collective
+        double seconds_reduce{};     // the all-reduce of the statistics itself, after the workers have stopped
         size_t frames{};
         size_t frame_iterations{};
         int gpus{};

@@ -532,6 +532,42 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     std::vector<std::vector<uint64_t>> gpu_stats(gpus, std::vector<uint64_t>(points_total * stats_width, 0));
     std::vector<double> point_seconds(points_total, 0.);
     double startup_seconds = 0., device_seconds = 0.;
+    // NCCL communicator set-up (seconds on an 8-GPU box) starts NOW on a side thread, beside the CUDA start-up of the devices
+    // that the workers are about to trigger, and the workers take their first batch only when it is done: set-up next to busy
+    // GPUs was measured to take 3x longer (its device-synchronising calls queue behind the persistent decode kernels: 10.9 s
+    // instead of ~3 s beside fp64 batches on 2 GPUs) and to slow the decoding by 4-15 %. So start-up = CUDA contexts + NCCL
+    // communicators, in parallel; after it the GPUs only decode. The sweep's one collective runs after the workers have stopped.
+    const bool reduce_over_nccl = !traced && (gpus > 1 || CFG.DEVICE_FORCE_ALLREDUCE);
+    std::thread comm_thread;
+    struct join_on_exit
+    {
+        std::thread &t;
+        ~join_on_exit()
+        {
+            if (t.joinable())
+                t.join();
+        }
+    } comm_joiner{comm_thread}; // an exception on the way must not destroy a running thread
+    std::string comm_error;
+    double comm_seconds = 0.;
+    std::atomic<bool> comm_ready{!reduce_over_nccl};
+    std::mutex comm_mu;
+    std::condition_variable comm_cv;
+    if (reduce_over_nccl)
+        comm_thread = std::thread([&]
+                                  {
+            const auto t0 = clock::now();
+            std::vector<int32_t> devices(gpus);
+            for (int g = 0; g < gpus; ++g)
+                devices[g] = g;
+            if (qlb_stats_comm_prepare(devices.data(), gpus) != QLB_OK)
+                comm_error = qlb_last_error();
+            comm_seconds = seconds_since(t0);
+            {
+                std::lock_guard<std::mutex> lk(comm_mu);
+                comm_ready = true;
+            }
+            comm_cv.notify_all(); });
 
     if (traced)
     {
@@ -604,6 +640,10 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 qlb_ctx *ctx = nullptr;
                 try { ctx = qkd_b200::context(g % gpus); } // worker g drives GPU g % gpus with its own context
                 catch (const std::exception &e) { record_error(e.what()); }
+                {
+                    std::unique_lock<std::mutex> lk(comm_mu);
+                    comm_cv.wait(lk, [&] { return comm_ready.load(); });
+                }
                 if (++contexts_ready == workers)
                     startup_seconds = seconds_since(t_start);
                 std::vector<uint32_t> iterations;
@@ -654,6 +694,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                     const size_t pt = b->point;
                     if (!b->on_device)
                         free_batches.push(b);
+
                     if (p.batches_left.fetch_sub(1, std::memory_order_acq_rel) == 1) // every worker's share of this point is in
                     {
                         std::lock_guard<std::mutex> lk(done_mu);
@@ -682,6 +723,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
                 std::unique_lock<std::mutex> lk(done_mu);
                 for (;;)
                 {
+
                     while (flushed < finished.size())
                     {
                         const size_t pt = finished[flushed++];
@@ -749,20 +791,27 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
         catch (...)
         {
             shut_down();
+            if (comm_thread.joinable())
+                comm_thread.join();
             throw;
         }
         shut_down();
+        if (comm_thread.joinable())
+            comm_thread.join();
         if (failed)
             throw std::runtime_error(first_error);
+        if (!comm_error.empty())
+            throw std::runtime_error("qlb_stats_comm_prepare: " + comm_error);
         device_seconds = device_ns.load() * 1e-9 / workers;
     }
 
     // ---- the sweep's one collective: SUM all-reduce of [points x (max_it + 5)] integers over the GPUs of this box -----------
-    // Communicators are created here, on this thread, after every worker has stopped: NCCL set-up next to threads that launch
-    // kernels and (re)allocate device buffers is the documented multi-thread deadlock pattern.
-    const bool reduce_over_nccl = !traced && (gpus > 1 || CFG.DEVICE_FORCE_ALLREDUCE);
+    // It runs here, after every worker has stopped (a collective kernel next to threads that launch persistent decode kernels is
+    // the documented multi-thread deadlock pattern); the communicators are normally ready by now (side thread above).
+    double reduce_seconds = 0.;
     if (reduce_over_nccl)
     {
+        const auto t_reduce = clock::now();
         std::vector<qlb_ctx *> ctxs;
         std::vector<uint64_t *> ptrs;
         for (int g = 0; g < gpus; ++g)
@@ -771,6 +820,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
             ptrs.push_back(gpu_stats[g].data());
         }
         qkd_b200::check(qlb_stats_allreduce(ctxs.data(), gpus, ptrs.data(), gpu_stats[0].size()), "qlb_stats_allreduce");
+        reduce_seconds = seconds_since(t_reduce);
     }
     else
         for (int g = 1; g < gpus; ++g)
@@ -800,6 +850,8 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const std::vector<sim_input> &
     g_report.seconds_total = seconds_since(t_start);
     g_report.seconds_device = device_seconds;
     g_report.seconds_startup = startup_seconds; // CUDA initialisation + contexts: ~1 s on a 1-GPU box, ~7 s on an 8-GPU box
+    g_report.seconds_comm_setup = comm_seconds;
+    g_report.seconds_reduce = reduce_seconds;
     g_report.frames = frames_total;
     g_report.frame_iterations = iterations_total;
     g_report.gpus = gpus;
