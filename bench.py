@@ -415,9 +415,11 @@ def main():
         "frame_iterations_per_s": fi_per_s, "edge_iterations_per_s": fi_per_s * e,
         "kernel_ms_per_step": kern_ms_step, "kernel_share_of_step": kern_ms_step / ms_step,
         "algorithmic_hbm": rf["algorithmic_hbm"], "secondary": [r for r in sm_roofs if r is not primary],
-        "note": "SM-resident decoder: a frame's messages stay in shared memory (fp64: 2 x 120 KB over a thread-block cluster / 92 % + an L2-resident tail), "
-                "so DRAM traffic is far below the algorithmic bytes and the binding roof is on the SM. `frac` is the SM-side roof measured as "
-                "(ncu warp instructions per frame-iteration of this build) x (live frame-iterations/s) / (slots x SMs x SM clock under load); "
+        "note": "SM-resident decoder: a frame's messages stay on the SM (fp32: all of them in shared memory; fp64: 92 % in shared memory + an "
+                "L2-resident tail per CTA), so DRAM traffic (`traffic`, ncu) is far below the algorithmic bytes and the binding roof is on the SM. "
+                "`frac` is the tighter of the two SM-side roofs: instruction issue = (ncu warp instructions per frame-iteration of this build) x "
+                "(live frame-iterations/s) / (4 issue slots x SMs x SM clock under load), and the FP64 pipe = the same with the FP64 warp "
+                "instructions against the DFMA rate measured on this GPU type (scripts/micro/fp64_peak.cu: 58 lanes per SM and clock). "
                 "`algorithmic_hbm.frac` is SURVEY.md 8d's fixed figure, the one north_star's 60 % target is quoted on.",
     }
     per_qber = []
@@ -554,6 +556,7 @@ def main():
                               "fer": 1.0 - float(((bres & 3) == 3).sum().item()) / fr,
                               "frame_iterations_per_s": its / (best * 1e-3), "edge_iterations_per_s": its * big.e / (best * 1e-3),
                               "achieved_GBps": gbs, "roofline_frac": gbs / hbm_peak, "bound": "hbm",
+                              "kernels": "qlb::stream_{setup,init,check,update,bit,repack_*,finalize}_kernel<%s>" % ("StreamF64" if precision.startswith("f64") else "StreamF32"),
                               "traffic": prof.get(name, {}).get("dram_bytes_per_launch"),
                               "note": "whole call incl. set-up and result kernels, CUDA events on the launching stream, best of %d" % reps}
             del ba, bb, blp, bit_, bres, big_code
@@ -567,12 +570,14 @@ def main():
             # a waterfall QBER: most frames converge around round 45, ~7 % run to 100 -- what the on-device frame compaction is
             # for (algorithmic bytes count only the rounds each frame needed)
             stream_case("stream_n100k_waterfall", big, 18944, 0.085, MAX_IT, "f32fast", 2, lbl + ", 18944 frames, QBER 0.085, max 100 iterations")
-            stream_case("stream_n100k_f64", big, 9472, 0.10, 20, "f64", 3, lbl + ", 9472 frames, QBER 0.10, 20 iterations, fp64 reference order")
+            stream_case("stream_n100k_f64", big, 9472, 0.10, 20, "f64", 3, lbl + ", 9472 frames, QBER 0.10, 20 iterations, fp64 reference order (fp64 streaming decoder)")
+            stream_case("stream_n100k_f64fused", big, 9472, 0.10, 20, "f64fused", 3, lbl + ", 9472 frames, QBER 0.10, 20 iterations, fp64 fused-ratio rule (fp64 streaming decoder)")
+            stream_case("stream_n100k_f64_waterfall", big, 9472, 0.085, MAX_IT, "f64", 1, lbl + ", 9472 frames, QBER 0.085, max 100 iterations, fp64 reference order")
             del big
             huge = codes.permutation_code(1_000_000, 510_800, 3, 666)
             lbl = "configs[3]: permutation code N=1000000 M=510800 CW=3 SEED=666"
             stream_case("stream_n1m", huge, 8192, 0.10, 12, "f32fast", 2, lbl + ", 8192 frames, QBER 0.10, 12 iterations, fp32 fast rule")
-            stream_case("stream_n1m_f64", huge, 4096, 0.10, 12, "f64", 2, lbl + ", 4096 frames, QBER 0.10, 12 iterations, fp64 reference order")
+            stream_case("stream_n1m_f64", huge, 4096, 0.10, 12, "f64", 2, lbl + ", 4096 frames, QBER 0.10, 12 iterations, fp64 reference order (fp64 streaming decoder)")
             del huge
         except Exception as ex:  # the headline line must not depend on the side measurements
             variants["stream_error"] = {"error": str(ex)[:300]}
