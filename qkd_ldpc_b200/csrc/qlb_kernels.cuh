@@ -26,7 +26,7 @@
 
 namespace qlb
 {
-    constexpr int kMaxCW = 64;
+    constexpr int kMaxCW = 128;
 
     // -DQLB_BOUNDS_CHECK: the kernels test the indices they are about to use (message slots, frame columns, scratch offsets) and
     // trap on the first one out of range -- the stand-in for compute-sanitizer's memcheck, which is closed on the B200 pool

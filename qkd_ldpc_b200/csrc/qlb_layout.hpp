@@ -27,7 +27,7 @@
 
 namespace qlb
 {
-    constexpr int kMaxCheckWeight = 64; // cnt[]/base[] travel in kernel parameters
+    constexpr int kMaxCheckWeight = 128; // cnt[]/base[] travel in kernel parameters (2 x 512 B)
     constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 
     struct CodeLayout

@@ -266,12 +266,24 @@ namespace qlb
                     else
                         pv[j] = prior; // unclamped (:182-190)
                 }
-#pragma unroll
-                for (int a = 0; a < kBW; ++a)
+                if constexpr (kBW > 0)
                 {
-                    QLB_CHECK_INDEX(code.bit_slots32[(size_t)a * n + i], code.slots);
-                    VecIO<Real, VEC>::store(sg.msg + VEC * lane + (size_t)(code.bit_slots32[(size_t)a * n + i] * sg.row_stride), pv);
+#pragma unroll
+                    for (int a = 0; a < kBW; ++a)
+                    {
+                        QLB_CHECK_INDEX(code.bit_slots32[(size_t)a * n + i], code.slots);
+                        VecIO<Real, VEC>::store(sg.msg + VEC * lane + (size_t)(code.bit_slots32[(size_t)a * n + i] * sg.row_stride), pv);
+                    }
                 }
+                else // any bit weights: the bit's list ends at the first empty entry
+                    for (int a = 0; a < code.max_bit_w; ++a)
+                    {
+                        const uint32_t slot = code.bit_slots32[(size_t)a * n + i];
+                        if (slot == 0xFFFFFFFFu)
+                            break;
+                        QLB_CHECK_INDEX(slot, code.slots);
+                        VecIO<Real, VEC>::store(sg.msg + VEC * lane + (size_t)(slot * sg.row_stride), pv);
+                    }
                 if (lane == 0)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j)
@@ -508,6 +520,79 @@ namespace qlb
         }
     }
 
+    // The same for a bit of ANY weight (irregular codes): nothing is held in registers between the sum and the extrinsic values --
+    // the rows are read twice, the second time from L2 (they were fetched a moment ago), so the HBM traffic is unchanged.
+    template <typename P, bool kReconcile, int VEC>
+    __device__ __forceinline__ void split_bit_any_weight(const DecodeArgs &args, const SplitGroup<typename P::real> &sg, int i, int lane,
+                                                         const typename P::real (&lp)[VEC], const uint32_t (&act_word)[VEC], const uint32_t (&fr)[VEC],
+                                                         typename P::real unit, typename P::real cap, bool clamp_b2c)
+    {
+        typedef typename P::real Real;
+        const CodeDev &code = args.code;
+        const int n = code.n;
+        QLB_CHECK_INDEX(i, n);
+        Real total[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+            if (kReconcile)
+                total[j] = stream_signed(lp[j], (sg.bobT[(size_t)i * VEC + j] >> lane) & 1u);
+            else if constexpr (P::kLsbDecision)
+                total[j] = fr[j] != kNoFrame ? __fmul_rn(unit, (float)args.llr[(size_t)fr[j] * n + i]) : 0.f;
+            else
+                total[j] = fr[j] != kNoFrame ? args.llr[(size_t)fr[j] * n + i] : 0.;
+        }
+        for (int a = 0; a < code.max_bit_w; ++a) // left to right from the prior, in the bit's arrival order (:256-258)
+        {
+            const uint32_t slot = code.bit_slots32[(size_t)a * n + i];
+            if (slot == 0xFFFFFFFFu)
+                break;
+            QLB_CHECK_INDEX(slot, code.slots);
+            Real c[VEC];
+            VecIO<Real, VEC>::load(sg.msg + VEC * lane + (size_t)(slot * sg.row_stride), c);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                total[j] = total[j] + c[j];
+        }
+        uint32_t zbits = 0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            zbits |= (uint32_t)(total[j] <= Real(0)) << j; // :259-266
+        for (int a = 0; a < code.max_bit_w; ++a)
+        {
+            const uint32_t slot = code.bit_slots32[(size_t)a * n + i];
+            if (slot == 0xFFFFFFFFu)
+                break;
+            Real *row = sg.msg + VEC * lane + (size_t)(slot * sg.row_stride);
+            Real c[VEC], o[VEC];
+            VecIO<Real, VEC>::load(row, c);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+            {
+                Real v = total[j] - c[j]; // :300-311
+                if constexpr (P::kLsbDecision)
+                {
+                    if (clamp_b2c)
+                        v = fminf(fmaxf(v, -cap), cap);
+                    o[j] = __uint_as_float((__float_as_uint(v) & ~1u) | ((zbits >> j) & 1u));
+                }
+                else
+                    o[j] = clamp_f64(v, cap);
+            }
+            VecIO<Real, VEC>::store(row, o);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+            const uint32_t word = __ballot_sync(0xffffffffu, (zbits >> j) & 1u);
+            if (lane == 0)
+            {
+                const size_t at = (size_t)i * VEC + j;
+                sg.zT[at] = (sg.zT[at] & ~act_word[j]) | (word & act_word[j]);
+            }
+        }
+    }
+
     template <typename P, bool kReconcile, int kBW, int VEC>
     __global__ void __launch_bounds__(kSplitBitThreads, QLB_SPLIT_BIT_MINB) stream_bit_kernel(const DecodeArgs args, const SplitState st)
     {
@@ -551,22 +636,31 @@ namespace qlb
             }
             if (!alive)
                 continue;
-            constexpr int U = QLB_SPLIT_BIT_U;
-            int i = i0 + warp / B;
-#pragma unroll 1
-            for (; i + (U - 1) * step < i1; i += U * step)
+            if constexpr (kBW == 0)
             {
-                int many[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    many[u] = i + u * step;
-                split_bits<P, kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, fr, unit, cap, clamp_b2c);
+#pragma unroll 1
+                for (int i = i0 + warp / B; i < i1; i += step)
+                    split_bit_any_weight<P, kReconcile, VEC>(args, sg, i, lane, lp, act_word, fr, unit, cap, clamp_b2c);
             }
-#pragma unroll 1
-            for (; i < i1; i += step)
+            else
             {
-                const int one[1] = {i};
-                split_bits<P, kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, fr, unit, cap, clamp_b2c);
+                constexpr int U = QLB_SPLIT_BIT_U;
+                int i = i0 + warp / B;
+#pragma unroll 1
+                for (; i + (U - 1) * step < i1; i += U * step)
+                {
+                    int many[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        many[u] = i + u * step;
+                    split_bits<P, kReconcile, kBW, VEC, U>(args, sg, many, lane, lp, act_word, fr, unit, cap, clamp_b2c);
+                }
+#pragma unroll 1
+                for (; i < i1; i += step)
+                {
+                    const int one[1] = {i};
+                    split_bits<P, kReconcile, kBW, VEC, 1>(args, sg, one, lane, lp, act_word, fr, unit, cap, clamp_b2c);
+                }
             }
         }
     }

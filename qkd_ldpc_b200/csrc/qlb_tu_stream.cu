@@ -129,16 +129,17 @@ namespace
         case 4: return launch_stream_vec<P, kReconcile, 4>(ctx, args);
 #endif
         case 3: return launch_stream_vec<P, kReconcile, 3>(ctx, args);
-        default: return fail(QLB_ERR_UNSUPPORTED, "streaming decoder: unsupported bit weight");
+        default: return launch_stream_vec<P, kReconcile, 0>(ctx, args); // irregular or heavier bits: the any-weight bit pass
         }
     }
 }
 namespace qlb
 {
-    // uniform column weight 2, 3 or 4 (BASELINE.json's code family is CW = 3); irregular bit weights take the generic kernel
+    // any bit weights (uniform 2 / 3 / 4 -- BASELINE.json's code family is CW = 3 -- through register-tiled instantiations of the bit
+    // pass, everything else through the any-weight form); check weights up to 16
     bool stream_eligible(const CodeDev &c)
     {
-        return c.uniform_bit_w >= 2 && c.uniform_bit_w <= 4 && c.max_check_w <= kResidentMaxCW && c.m <= c.n && c.col_of_slot32 != nullptr;
+        return c.max_bit_w >= 1 && c.max_check_w <= kResidentMaxCW && c.m <= c.n && c.col_of_slot32 != nullptr;
     }
     int launch_stream_f32(qlb_ctx *ctx, DecodeArgs &args, bool reconcile, bool fast)
     {

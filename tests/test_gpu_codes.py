@@ -261,3 +261,83 @@ def test_streaming_other_bit_weights(ctx, oracle, dv):
             st = ctx.reconcile_packed(code, capi.make_params(32, 30, 100.0, True, fast_math=fast, tier=3), a, b, Q)
             assert ((gen[1] & 3) == (st[1] & 3)).mean() >= 0.98, (dv, q, fast)
             assert (np.abs(gen[0].astype(int) - st[0].astype(int)) <= 1).mean() >= 0.95
+
+
+def test_high_rate_code_check_weight_80(ctx, oracle):
+    """config.json's code_rate 0.95 preset at column weight 4 means check weight 80 (the layout used to stop at 64). A
+    permutation code N = 4 000, M = 200: fp64 must equal the oracle frame by frame (generic kernel, two-pass rule over 80 edges),
+    fp32 must agree on the flags."""
+    n, m = 4000, 200
+    mat = codes.permutation_code(n, m, 4, 99)
+    assert int(np.diff(mat.row_ptr).max()) == 80
+    g, code = graph_of(mat), capi.Code.from_graph(mat)
+    seeds = oracle.trial_seeds(5, 64)
+    seen = set()
+    for q in (0.002, 0.004):
+        want, wdec = oracle.run_trials(g, q, seeds, threads=8, max_it=30, want_decoded=True)
+        a, b, ex = ctx.generate(n, seeds, q)
+        Q = np.full(len(seeds), ex)
+        seen |= set(want[:, 1].tolist())
+        for fused in (False, True):
+            it, res, dec, syn = ctx.reconcile_packed(code, capi.make_params(64, 30, 100.0, True, fast_math=fused), a, b, Q, want_decoded=True, want_syndrome=True)
+            assert (capi.unpack_bits(syn, m) == np.stack([oracle.syndrome(g, x) for x in capi.unpack_bits(a, n)])).all()
+            assert ((res & 1) == want[:, 1]).all() and (((res >> 1) & 1) == want[:, 2]).all() and (it == want[:, 0]).all(), (q, fused)
+            assert (capi.unpack_bits(dec, n) == wdec).all()
+        it, res, _, _ = ctx.reconcile_packed(code, capi.make_params(32, 30, 100.0, True), a, b, Q)
+        assert ((res & 3) == (want[:, 1] | (want[:, 2] << 1))).mean() >= 0.9
+    assert seen == {0, 1}
+
+
+def irregular_code(n, m, seed):
+    """A seeded code with column weights 2 / 3 / 4 / 6 (40 / 35 / 15 / 10 %) and near-equal check weights: every bit draws its
+    checks from a shuffled pool in which each check appears equally often; duplicates inside a bit are re-drawn."""
+    rng = np.random.default_rng(seed)
+    w = rng.choice([2, 3, 4, 6], size=n, p=[0.40, 0.35, 0.15, 0.10])
+    e = int(w.sum())
+    pool = np.resize(rng.permutation(m), e)
+    rng.shuffle(pool)
+    h = np.zeros((m, n), np.uint8)
+    at = 0
+    for i in range(n):
+        picks = set()
+        for c in pool[at:at + w[i]]:
+            c = int(c)
+            while c in picks:
+                c = int(rng.integers(m))
+            picks.add(c)
+        at += w[i]
+        h[sorted(picks), i] = 1
+    assert (h.sum(1) >= 2).all()
+    return codes.Matrix.from_dense(h, f"irregular_n{n}_m{m}_seed{seed}")
+
+
+def test_streaming_irregular_bit_weights(ctx, oracle):
+    """Irregular column weights (2 / 3 / 4 / 6) through the streaming decoder's any-weight bit pass (forced with the tier-3 hook;
+    N = 2 048, check weights <= 16): fp64, both rules, must equal the oracle frame by frame -- iterations, flags, every decoded bit,
+    syndromes -- on 200 frames that straddle the code's threshold, through repacks and in the <= 32-frame form; fp32 must agree
+    with the generic fp32 kernel on the flags."""
+    n, m = 2048, 1024
+    mat = irregular_code(n, m, 12)
+    assert mat.max_check_w <= 16 and len(set(np.diff(mat.col_ptr).tolist())) >= 3
+    g, code = graph_of(mat), capi.Code.from_graph(mat)
+    seeds = oracle.trial_seeds(77, 200)
+    seen = set()
+    for q in (0.02, 0.08, 0.10):
+        want, wdec = oracle.run_trials(g, q, seeds, threads=8, max_it=40, want_decoded=True)
+        seen |= set(want[:, 1].tolist())
+        a, b, ex = ctx.generate(n, seeds, q)
+        Q = np.full(len(seeds), ex)
+        want_syn = np.stack([oracle.syndrome(g, x) for x in capi.unpack_bits(a, n)])
+        for fused in (False, True):
+            for cnt in (200, 20):
+                it, res, dec, syn = ctx.reconcile_packed(code, capi.make_params(64, 40, 100.0, True, fast_math=fused, tier=3), a[:cnt], b[:cnt], Q[:cnt],
+                                                         want_decoded=True, want_syndrome=True)
+                assert (capi.unpack_bits(syn, m) == want_syn[:cnt]).all()
+                assert ((res & 1) == want[:cnt, 1]).all() and (((res >> 1) & 1) == want[:cnt, 2]).all(), (q, fused, cnt)
+                assert (it == want[:cnt, 0]).all(), (q, fused, cnt, np.flatnonzero(it != want[:cnt, 0])[:8])
+                assert (capi.unpack_bits(dec, n) == wdec[:cnt]).all()
+        for fast in (False, True):
+            gen = ctx.reconcile_packed(code, capi.make_params(32, 40, 100.0, True, fast_math=fast, tier=2), a, b, Q)
+            st = ctx.reconcile_packed(code, capi.make_params(32, 40, 100.0, True, fast_math=fast, tier=3), a, b, Q)
+            assert ((gen[1] & 3) == (st[1] & 3)).mean() >= 0.97, (q, fast)
+    assert seen == {0, 1}
