@@ -344,3 +344,25 @@ def test_no_clamp_nan_semantics(ctx, dev_codes, graphs, oracle, tier):
         wit, wok, wbits = oracle.sum_product(g, llr, syn, 30, 100.0, en, precision=64)
         it, res, bits = ctx.sum_product(code, capi.make_params(64, 30, 100.0, en, tier=tier), llr[None], syn[None])
         assert it[0] == wit and bool(res[0] & 1) == wok and (bits[0] == wbits).all(), (en, tier, it, wit)
+
+
+@pytest.mark.gpu
+def test_gpu_against_the_reference_library_itself(ctx, dev_codes, reference):
+    """No restatement in the chain: the unmodified reference (oracle/_ref/libqkdref.so -- it travels to the GPU box with the
+    snapshot) runs run_trial on the host for fresh seeds while the GPU decodes the same trials through qlb_run_trials; fp64 (both
+    rules): iterations and flags equal on every frame; fp32: same flags. Skipped only where oracle/_ref was never built."""
+    from qkd_ldpc_b200 import codes
+    h = reference.load(codes.materialize()[NS], dense=False)
+    try:
+        seeds = reference.trial_seeds(20261019, 48)
+        for pt, (q, k) in enumerate(((0.03, 48), (0.07, 48), (0.0825, 24), (0.0875, 12), (0.10, 6))):
+            out = reference.run_trials(h, q, seeds[:k] + np.uint64(pt), threads=16)
+            want_fl = (out[:, 1] | (out[:, 2] << np.uint64(1))).astype(np.int64)
+            for precision, fast in ((64, False), (64, True), (32, False), (32, True)):
+                it, res, _ = ctx.run_trials(dev_codes[NS], capi.make_params(precision, 100, 100.0, True, fast_math=fast), seeds[:k], q, seed_offset=pt)
+                if precision == 64:
+                    assert ((res & 3) == want_fl).all() and (it.astype(np.int64) == out[:, 0].astype(np.int64)).all(), (q, fast)
+                else:
+                    assert ((res & 3) == want_fl).mean() >= (1.0 if q < 0.08 or q >= 0.1 else 0.9), (q, fast)
+    finally:
+        reference.free(h)
