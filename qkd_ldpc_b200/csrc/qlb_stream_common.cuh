@@ -38,7 +38,10 @@ namespace qlb
         typedef double real;
         typedef Math_ Math;
         static constexpr bool kLsbDecision = false;
-        static constexpr int kVecWide = 2;
+#ifndef QLB_STREAM64_VEC
+#define QLB_STREAM64_VEC 2
+#endif
+        static constexpr int kVecWide = QLB_STREAM64_VEC;
     };
 
     template <typename Real, int VEC>

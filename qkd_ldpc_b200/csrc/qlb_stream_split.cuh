@@ -52,6 +52,14 @@ namespace qlb
         static constexpr int kCheckThreads = P::kLsbDecision ? QLB_SPLIT_CHECK_THREADS : QLB_SPLIT64_CHECK_THREADS;
         static constexpr int kCheckMinB = P::kLsbDecision ? QLB_SPLIT_CHECK_MINB : QLB_SPLIT64_CHECK_MINB;
         static constexpr int kCheckChunk = 8 * (kCheckThreads / 32); // sorted check positions per work item
+#ifndef QLB_SPLIT64_BIT_U
+#define QLB_SPLIT64_BIT_U QLB_SPLIT_BIT_U
+#endif
+#ifndef QLB_STREAM64_BUNDLE
+#define QLB_STREAM64_BUNDLE 4
+#endif
+        static constexpr int kBitU = P::kLsbDecision ? QLB_SPLIT_BIT_U : QLB_SPLIT64_BIT_U; // bits per warp in flight
+        static constexpr int kBundle = P::kLsbDecision ? 4 : QLB_STREAM64_BUNDLE;           // groups per bundle
     };
     constexpr int kSplitBitChunk = 16 * (kSplitBitThreads / 32);    // bits per work item
 
@@ -644,7 +652,7 @@ namespace qlb
             }
             else
             {
-                constexpr int U = QLB_SPLIT_BIT_U;
+                constexpr int U = SplitTune<P>::kBitU;
                 int i = i0 + warp / B;
 #pragma unroll 1
                 for (; i + (U - 1) * step < i1; i += U * step)

@@ -13,7 +13,7 @@ namespace
         typedef typename P::real Real;
         const long long G = 32 * VEC, groups = (args.n_frames + G - 1) / G;
         // groups per bundle: 2 KB of contiguous memory per slot when there are enough groups (see qlb_stream_split.cuh)
-        int B = VEC == P::kVecWide ? 4 : 1; // measured on B200, N = 100 000, fp32: B = 1 / 2 / 4 / 8 -> 0.589 / 0.668 / 0.789 / 0.783 of the copy bandwidth
+        int B = VEC == P::kVecWide ? SplitTune<P>::kBundle : 1; // measured on B200, N = 100 000, fp32: B = 1 / 2 / 4 / 8 -> 0.589 / 0.668 / 0.789 / 0.783 of the copy bandwidth
         while (B > 1 && (groups < B || (unsigned long long)args.code.slots * B * G >= 0xFFFFFFFFull)) // row offsets are 32-bit
             B /= 2;
         if ((unsigned long long)args.code.slots * B * G >= 0xFFFFFFFFull)

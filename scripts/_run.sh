@@ -1,4 +1,9 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "reference_library_itself" 2>&1 | tail -3
-export QLB_LIBRARY=$PWD/qkd_ldpc_b200/lib/variants/liblibm.so
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_codes.py -m gpu -x -q -k "(campaign and f64) or golden or waterfall_fp64 or no_clamp or edge_cases or small_codes or kat or streaming_fp64 or reference_library_itself" > gpurun_out/r2x_libm_forms.log 2>&1; tail -5 gpurun_out/r2x_libm_forms.log
-python scripts/profile_point.py f64 0.09 2960 | tail -1 >> gpurun_out/r2x_libm_forms.log; tail -1 gpurun_out/r2x_libm_forms.log
+for v in "" v1b8 v1b4 v1b8c2 v1b8c4; do
+  echo "== variant ${v:-base}"
+  if [ -n "$v" ]; then export QLB_LIBRARY=$PWD/qkd_ldpc_b200/lib/variants/lib$v.so; else unset QLB_LIBRARY; fi
+  timeout 300 python scripts/stream_probe.py 100000 51080 9472 0.10 20 f64 2>&1 | tail -1
+  timeout 300 python scripts/stream_probe.py 100000 51080 9472 0.10 20 f64fused 2>&1 | tail -1
+done > gpurun_out/r2y_variants.log 2>&1
+cat gpurun_out/r2y_variants.log
+export QLB_LIBRARY=$PWD/qkd_ldpc_b200/lib/variants/libv1b8.so
+python -m pytest tests/test_gpu_codes.py -m gpu -x -q -k "streaming_fp64 or block_length or large_block" 2>&1 | tail -3
