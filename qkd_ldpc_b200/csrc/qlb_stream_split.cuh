@@ -4,7 +4,7 @@
 //
 //     setup init | check(0) update(0) bit | check(1) update(1) bit | ... | check(max_it) update(max_it) | finalize
 //
-// Why: the persistent one-CTA-per-group kernel ties a group to one SM for its whole life -- it needs as many groups as SMs
+// Why: a persistent one-CTA-per-group kernel (the first version, retired) ties a group to one SM for its whole life -- it needs as many groups as SMs
 // (N = 1 000 000: HBM holds 99 groups, so 49 SMs idle), the last groups of a launch run on a mostly empty chip, and one
 // register budget (128) has to serve both passes, capping the bit pass at 16 warps per SM although it is pure gather/scatter.
 // Here work items are (group, chunk of consecutive nodes), spread evenly over a grid sized to the SM count; the check kernel
@@ -16,7 +16,8 @@
 // handled by adjacent warps of one CTA. The bit pass is a random gather of rows; with B = 4 the unit the DRAM sees is 2 KB
 // instead of 512 B (measured on B200, N = 100 000: bit kernel 3.4 TB/s at B = 1 against 5.4 TB/s for the sequential check
 // kernel -- row-buffer locality, not occupancy, is what the gather lacks). Bookkeeping stays per group.
-// Results are bit-identical to the persistent kernel and to the SM-resident kernel (tests/test_gpu_codes.py).
+// Results are identical to the SM-resident kernels of the same precision, frame by frame (tests/test_gpu_codes.py). fp32 and fp64 share
+// every kernel here through a precision policy (StreamF32<Rule> / StreamF64<Math>, qlb_stream_common.cuh).
 #pragma once
 #include "qlb_stream_common.cuh"
 
