@@ -36,6 +36,7 @@ namespace qlb
         case 2: r = f64m::log_ratio(x, y); break;
         case 3: r = MathF64::tanh_half(x); break;
         case 4: r = MathF64::two_atanh(x, y != 0.); break;
+        case 5: r = f64m::exp_neg_abs(x); break;
         default: r = 0.; break;
         }
         out[i] = r;
@@ -804,7 +805,7 @@ extern "C"
     // ---- test probe of the fp64 building blocks -----------------------------------------------------------------------------
     int qlb_test_f64_math(qlb_ctx *ctx, int op, int64_t n, const double *a, const double *b, double *out)
     {
-        if (!ctx || n < 0 || op < 0 || op > 4 || (n > 0 && (!a || !out)))
+        if (!ctx || n < 0 || op < 0 || op > 5 || (n > 0 && (!a || !out)))
             return fail(QLB_ERR_INVALID, "qlb_test_f64_math: bad arguments");
         if (n == 0)
             return QLB_OK;
