@@ -366,3 +366,26 @@ def test_gpu_against_the_reference_library_itself(ctx, dev_codes, reference):
                     assert ((res & 3) == want_fl).mean() >= (1.0 if q < 0.08 or q >= 0.1 else 0.9), (q, fast)
     finally:
         reference.free(h)
+
+
+@pytest.mark.parametrize("tier", [None, 2, 3])
+def test_qber_one_half_zero_prior(ctx, dev_codes, graphs, oracle, tier):
+    """QBER = 0.5 passes the reference's config validation (src/config.cpp:88) and makes the a-priori LLR ln((1-q)/q) exactly 0:
+    tanh(0) = 0, row product 0, 0 / 0 = NaN on every edge. The device must follow the reference into that corner
+    -- same iteration count (max_it), same flags, same decoded bits (a NaN total decides 0) -- in the resident, the generic and
+    the streaming fp64 kernels, both rules, and the fp32 kernels must at least agree on the flags."""
+    g, code = graphs[NS], dev_codes[NS]
+    rng = np.random.default_rng(50)
+    a = rng.integers(0, 2, (40, g.n)).astype(np.int32)
+    b = a ^ (rng.random((40, g.n)) < 0.5).astype(np.int32)
+    want = [oracle.qkd_ldpc(g, a[k], b[k], 0.5, max_it=6) for k in range(4)]  # (iterations, syndromes_match, keys_match, syndrome, decoded)
+    for fused in (False, True):
+        it, res, dec, _ = ctx.reconcile_packed(code, capi.make_params(64, 6, 100.0, True, fast_math=fused, tier=tier), capi.pack_bits(a), capi.pack_bits(b),
+                                               np.full(40, 0.5), want_decoded=True)
+        for k in range(4):
+            assert (int(it[k]), int(res[k] & 1), int((res[k] >> 1) & 1)) == tuple(int(x) for x in want[k][:3]), (fused, k, it[k], res[k], want[k][:3])
+            assert (capi.unpack_bits(dec[k:k + 1], g.n)[0] == want[k][4]).all()
+        assert (it == it[0]).all() and (res == res[0]).all()
+    if tier in (None, 3):
+        it32, res32, _, _ = ctx.reconcile_packed(code, capi.make_params(32, 6, 100.0, True, tier=tier), capi.pack_bits(a), capi.pack_bits(b), np.full(40, 0.5))
+        assert ((res32 & 3) == (res & 3)).all()
