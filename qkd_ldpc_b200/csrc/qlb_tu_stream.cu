@@ -36,7 +36,11 @@ namespace
         st.bundles = static_cast<unsigned char *>(ctx->scratch.p);
         st.bundle_stride = per_bundle;
         st.bundle = B;
-        st.repack_pct = 65; // measured on B200, N = 100 000: 50 / 65 / 80 / 90 % -> 0.664 / 0.694 / 0.686 / 0.651 of peak at QBER 0.085
+#ifndef QLB_STREAM64_REPACK_PCT
+#define QLB_STREAM64_REPACK_PCT 65
+#endif
+        // measured on B200, N = 100 000, QBER 0.085, fp32: 50 / 65 / 80 / 90 % -> 0.664 / 0.694 / 0.686 / 0.651 of peak; fp64: 0.442 / 0.465 / 0.472 / 0.368
+        st.repack_pct = P::kLsbDecision ? 65 : QLB_STREAM64_REPACK_PCT;
         uint32_t *words = reinterpret_cast<uint32_t *>(st.bundles + (size_t)bundles_per_wave * per_bundle);
         st.act = words;
         st.bad = words + 4 * per_wave;
