@@ -159,11 +159,23 @@ namespace qlb
             j -= (u * 65536u < d * 46341u) ? 1 : 0; // u / d < sqrt(1/2)
             const double ds = __hiloint2double(hd + (j << 20), __double2loint(den));
             const double s = div_pos(num - ds, num + ds);
-            const double z = s * s, w = z * z;
+            const double z = s * s;
+#ifdef QLB_F64_LOG_SPLIT_POLY // fdlibm's even / odd split (two shorter chains, two FP64 operations more)
+            const double w = z * z;
             const double t1 = w * fma(w, fma(w, kLg[5], kLg[3]), kLg[1]);
             const double t2 = z * fma(w, fma(w, fma(w, kLg[6], kLg[4]), kLg[2]), kLg[0]);
+            const double R = t2 + t1;
+#else // Horner: the check rule is bound by the FP64 pipe's throughput, not by this chain's latency (six independent edges per check)
+            double R = fma(z, kLg[6], kLg[5]);
+            R = fma(z, R, kLg[4]);
+            R = fma(z, R, kLg[3]);
+            R = fma(z, R, kLg[2]);
+            R = fma(z, R, kLg[1]);
+            R = fma(z, R, kLg[0]);
+            R = z * R;
+#endif
             const double dj = (double)j;
-            return fma(dj, kLn2Hi, fma(2., s, fma(s, t2 + t1, dj * kLn2Lo)));
+            return fma(dj, kLn2Hi, fma(2., s, fma(s, R, dj * kLn2Lo)));
         }
 
         // tanh(m / 2) = (1 - e^-|m|) / (1 + e^-|m|); |m| capped (exp_neg_abs; the quotient is exactly +-1 far earlier).
